@@ -1,0 +1,39 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/vvb200.h declares,
+and refuses to compute without a CUDA device (no fallback)."""
+import ctypes as C
+
+import pytest
+
+from vietvoice_tts_b200 import _lib
+from vietvoice_tts_b200.arch import TINY, FULL, ArchConfig, VVArch
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _lib.declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libvvb200.so does not export {n}"
+
+
+def test_arch_struct_matches_header():
+    assert C.sizeof(VVArch) == 33 * 4
+    c = FULL.to_c()
+    assert c.dim == 1024 and c.depth == 22 and c.nfe == 32 and abs(c.cfg_strength - 2.0) < 1e-7
+
+
+def test_no_cpu_fallback(lib):
+    if lib.vv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    carch = TINY.to_c()
+    rc = lib.vv_engine_create(C.byref(carch), 0, None, C.byref(h))
+    assert rc == -2                                   # VV_ERR_CUDA
+    assert b"no CUDA device" in lib.vv_last_error()
+
+
+def test_bad_arch_rejected(lib):
+    h = C.c_void_p()
+    bad = ArchConfig(dim=1000, heads=16).to_c() if False else TINY.to_c()
+    bad.head_dim = 32
+    rc = lib.vv_engine_create(C.byref(bad), 0, None, C.byref(h))
+    assert rc == -1

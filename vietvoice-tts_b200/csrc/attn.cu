@@ -1,0 +1,272 @@
+// Non-causal flash attention for sm_100a (d_h = 64), tcgen05 + TMEM.
+// One CTA = one head x 256 query rows (two 128-row tiles, each owned by one softmax warpgroup).
+//   S_t = Q_t K^T      : tcgen05.mma M128 N128 K64, accumulator in TMEM (128 cols per tile)
+//   softmax (online, lazy rescale) in registers: one thread per query row, no shuffles
+//   P_t -> bf16 in 128B-swizzled smem, O_t += P_t V : tcgen05.mma M128 N64 K128, V consumed MN-major straight
+//   from the TMA tile (no transpose), O accumulator in TMEM (64 cols per tile)
+// RoPE has already been applied to q/k by the QKV GEMM epilogue.
+//
+// Replaces the attention sub-graph of `transformer.onnx` (/root/reference/vietvoicetts/core/tts_engine.py:161-172).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vv {
+
+namespace attn {
+constexpr int KV_STAGES = 3;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+constexpr int Q_OFF = 0;                                   // 2 tiles
+constexpr int K_OFF = Q_OFF + 2 * TILE_BYTES;              // KV_STAGES tiles
+constexpr int V_OFF = K_OFF + KV_STAGES * TILE_BYTES;      // KV_STAGES tiles
+constexpr int P_OFF = V_OFF + KV_STAGES * TILE_BYTES;      // 2 tiles x 2 atoms
+constexpr int BAR_OFF = P_OFF + 4 * TILE_BYTES;
+constexpr int SMEM = BAR_OFF + 256 + 1024;
+constexpr int THREADS = 384;
+constexpr uint32_t TM_S = 0;     // S0 @0, S1 @128
+constexpr uint32_t TM_O = 256;   // O0 @256, O1 @320
+}  // namespace attn
+
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  using namespace attn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // KV_STAGES
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;  // 2
+  uint64_t* p_full = s_full + 2;           // 2
+  uint64_t* o_done = p_full + 2;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x % p.n_tiles;
+  const int head = blockIdx.x / p.n_tiles;
+  const int seq = p.tile_seq[tile];
+  const int q0 = p.tile_q0[tile];
+  const int seq_row0 = p.seq_off[seq];
+  const int kv_len = p.seq_len[seq];
+  const int n_kv = (kv_len + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      tma_load_2d(smem + Q_OFF, &tmQKV, head * 64, seq_row0 + q0, q_full);
+      tma_load_2d(smem + Q_OFF + TILE_BYTES, &tmQKV, head * 64, seq_row0 + q0 + 128, q_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], TILE_BYTES);
+        tma_load_2d(smem + K_OFF + stage * TILE_BYTES, &tmQKV, p.dim + head * 64, seq_row0 + j * 128, &k_full[stage]);
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        mbar_expect_tx(&v_full[stage], TILE_BYTES);
+        tma_load_2d(smem + V_OFF + stage * TILE_BYTES, &tmQKV, 2 * p.dim + head * 64, seq_row0 + j * 128,
+                    &v_full[stage]);
+        if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 1);
+      const uint32_t q_addr = smem_u32(smem + Q_OFF);
+      const uint32_t k_addr = smem_u32(smem + K_OFF);
+      const uint32_t v_addr = smem_u32(smem + V_OFF);
+      const uint32_t p_addr = smem_u32(smem + P_OFF);
+      auto issue_s = [&](int t, int stage) {
+        const uint64_t a0 = make_sdesc_sw128(q_addr + t * TILE_BYTES);
+        const uint64_t b0 = make_sdesc_sw128(k_addr + stage * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + TM_S + t * 128, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+      };
+      auto issue_pv = [&](int t, int stage, bool first) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t a = make_sdesc_sw128(p_addr + (2 * t + (k >> 2)) * TILE_BYTES) + 2 * (k & 3);
+          const uint64_t b = make_sdesc_sw128(v_addr + stage * TILE_BYTES + k * 2048);
+          umma_ss(tmem_base + TM_O + t * 64, a, b, idesc_o, !(first && k == 0));
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      umma_commit(&s_full[0]);
+      issue_s(1, 0);
+      umma_commit(&s_full[1]);
+      umma_commit(&k_empty[0]);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
+        const bool last = (j + 1 == n_kv);
+        mbar_wait(&v_full[stage], phase);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, stage, j == 0);
+        if (!last) {
+          mbar_wait(&k_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(0, nstage);
+          umma_commit(&s_full[0]);
+        } else {
+          umma_commit(&o_done[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, stage, j == 0);
+        umma_commit(&v_empty[stage]);
+        if (!last) {
+          issue_s(1, nstage);
+          umma_commit(&s_full[1]);
+          umma_commit(&k_empty[nstage]);
+        } else {
+          umma_commit(&o_done[1]);
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = warp >> 2;                 // q tile
+    const int r = threadIdx.x & 127;         // row within tile == TMEM lane
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t ts = tmem_base + lane_base + TM_S + t * 128;
+    const uint32_t to = tmem_base + lane_base + TM_O + t * 64;
+    uint8_t* prow = smem + P_OFF + (2 * t) * TILE_BYTES + r * 128;
+    const int sw = r & 7;
+    float m_ref = 0.0f, l = 0.0f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      const int kv_valid = kv_len - j * 128;
+      if (kv_valid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+      }
+      float mx = __uint_as_float(s[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      mx *= p.scale_log2;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool need = (mx - m_ref) > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx);
+          const float f = fast_exp2(m_ref - m_new);
+          m_ref = m_new;
+          l *= f;
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(to + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(to + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 columns (16 bytes of bf16)
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
+          sum += e[i];
+        }
+        uint4 u;
+        u.x = pack_bf16(e[0], e[1]);
+        u.y = pack_bf16(e[2], e[3]);
+        u.z = pack_bf16(e[4], e[5]);
+        u.w = pack_bf16(e[6], e[7]);
+        const int atom = c >> 3, chunk = c & 7;
+        *reinterpret_cast<uint4*>(prow + atom * TILE_BYTES + ((chunk ^ sw) << 4)) = u;
+      }
+      l += sum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    // ---- finalize: O / l -> bf16
+    mbar_wait(&o_done[t], 0);
+    tc_fence_after();
+    const int qrow = q0 + t * 128 + r;
+    const float inv = 1.0f / l;
+    bf16* orow = p.out + (size_t)(seq_row0 + qrow) * p.dim + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(to + c * 32, o);
+      tmem_ld_wait();
+      if (qrow < kv_len) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc(tmem_base, 512);
+}
+
+void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM);
+    attr_set = true;
+  }
+  if (p.n_tiles <= 0) return;
+  attn_kernel<<<p.n_tiles * p.heads, attn::THREADS, attn::SMEM, st>>>(tmQKV, p);
+}
+
+}  // namespace vv

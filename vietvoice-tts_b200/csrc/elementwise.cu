@@ -1,0 +1,174 @@
+// Bandwidth-bound row kernels of the DiT step: LayerNorm + AdaLN modulation (fp32 residual stream -> bf16 GEMM
+// operand), CFG combine + Euler update, and small fp32 helpers used once per engine / per utterance.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vv {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row, row kept in registers (dim <= 2048, dim % 128 == 0): one HBM read, one bf16 write.
+template <int VEC4_PER_LANE, bool AFFINE>
+__global__ void __launch_bounds__(256)
+ln_kernel(const float* __restrict__ x, int rows, int dim, const float* __restrict__ a, const float* __restrict__ b,
+          float eps, bf16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * dim);
+  float4 v[VEC4_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC4_PER_LANE; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC4_PER_LANE; ++i) {
+    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+#pragma unroll
+  for (int i = 0; i < VEC4_PER_LANE; ++i) {
+    const int c4 = lane + 32 * i;
+    // AFFINE: a = gamma, b = beta -> y = n*gamma + beta.  else: a = shift, b = scale -> y = n*(1+scale)+shift
+    float4 pa = __ldg(reinterpret_cast<const float4*>(a) + c4);
+    float4 pb = __ldg(reinterpret_cast<const float4*>(b) + c4);
+    float4 y;
+    if (AFFINE) {
+      y.x = (v[i].x - mean) * rstd * pa.x + pb.x;
+      y.y = (v[i].y - mean) * rstd * pa.y + pb.y;
+      y.z = (v[i].z - mean) * rstd * pa.z + pb.z;
+      y.w = (v[i].w - mean) * rstd * pa.w + pb.w;
+    } else {
+      y.x = (v[i].x - mean) * rstd * (1.f + pb.x) + pa.x;
+      y.y = (v[i].y - mean) * rstd * (1.f + pb.y) + pa.y;
+      y.z = (v[i].z - mean) * rstd * (1.f + pb.z) + pa.z;
+      y.w = (v[i].w - mean) * rstd * (1.f + pb.w) + pa.w;
+    }
+    if (out_bf16) {
+      uint2 u;
+      u.x = pack_bf16(y.x, y.y);
+      u.y = pack_bf16(y.z, y.w);
+      reinterpret_cast<uint2*>(out_bf16 + (size_t)row * dim)[c4] = u;
+    }
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * dim)[c4] = y;
+  }
+}
+
+template <bool AFFINE>
+static void launch_ln_any(const float* x, int rows, int dim, const float* a, const float* b, float eps, bf16* ob,
+                          float* of, cudaStream_t st) {
+  const int grid = (rows + 7) / 8;
+  if (grid == 0) return;
+  switch (dim / 128) {
+    case 1: ln_kernel<1, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 2: ln_kernel<2, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 4: ln_kernel<4, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 8: ln_kernel<8, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 12: ln_kernel<12, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 16: ln_kernel<16, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    default: break;  // validated by the engine: dim in {128,256,512,1024,1536,2048}
+  }
+}
+
+void launch_ln_mod(const float* x, int rows, int dim, const float* shift, const float* scale, float eps, bf16* out,
+                   cudaStream_t st) {
+  launch_ln_any<false>(x, rows, dim, shift, scale, eps, out, nullptr, st);
+}
+void launch_ln_affine(const float* x, int rows, int dim, const float* g, const float* b, float eps, bf16* out_bf16,
+                      float* out_f32, cudaStream_t st) {
+  launch_ln_any<true>(x, rows, dim, g, b, eps, out_bf16, out_f32, st);
+}
+
+// ---------------------------------------------------------------------------------- CFG + Euler
+__global__ void cfg_euler_kernel(float* __restrict__ noise, bf16* __restrict__ nb, int ld_nb,
+                                 const float* __restrict__ v, int ldv, const uint8_t* __restrict__ row_mask, int R,
+                                 int n_mel, float dt, float cfg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * n_mel) return;
+  const int r = idx / n_mel, c = idx - r * n_mel;
+  if (row_mask[r] == 0) return;
+  const float vc = v[(size_t)r * ldv + c];
+  const float vu = v[(size_t)(r + R) * ldv + c];
+  const float x = noise[idx] + dt * (vc + cfg * (vc - vu));
+  noise[idx] = x;
+  const bf16 xb = __float2bfloat16(x);
+  nb[(size_t)r * ld_nb + c] = xb;
+  nb[(size_t)(r + R) * ld_nb + c] = xb;
+}
+void launch_cfg_euler(float* noise, bf16* noise_bf16, int ld_nb, const float* v, int ldv, const uint8_t* row_mask,
+                      int R, int n_mel, float dt, float cfg, cudaStream_t st) {
+  const int n = R * n_mel;
+  if (n == 0) return;
+  cfg_euler_kernel<<<(n + 255) / 256, 256, 0, st>>>(noise, noise_bf16, ld_nb, v, ldv, row_mask, R, n_mel, dt, cfg);
+}
+
+// ---------------------------------------------------------------------------------- small fp32 linear
+// y[r, o] = act(sum_i x[r,i]*w[o,i] + b[o]); one warp per output element. Used only at engine build time
+// (time-embedding MLP and the per-step AdaLN modulation tables), never in the sampling loop.
+__global__ void linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ b, float* __restrict__ y, int rows, int in_f, int out_f,
+                                  int ldy, int act_silu) {
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (long)rows * out_f) return;
+  const int r = gw / out_f, o = gw % out_f;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)r * in_f;
+  const float* wr = w + (size_t)o * in_f;
+  float s = 0.f;
+  for (int i = lane; i < in_f; i += 32) s += xr[i] * wr[i];
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += b ? b[o] : 0.f;
+    if (act_silu) s = s / (1.f + __expf(-s));
+    y[(size_t)r * ldy + o] = s;
+  }
+}
+void launch_linear_f32(const float* x, const float* w, const float* b, float* y, int rows, int in_f, int out_f,
+                       int ldy, int act_silu, cudaStream_t st) {
+  const long warps = (long)rows * out_f;
+  if (warps == 0) return;
+  linear_f32_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(x, w, b, y, rows, in_f, out_f, ldy, act_silu);
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = __float2bfloat16(s[i]);
+}
+void launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
+}
+
+// dst[r, c] = c < cols ? bf16(src[r*ld_src + c]) : 0   for c < dst_cols  (zero-pads K up to a multiple of 64)
+__global__ void f32_to_bf16_2d_kernel(const float* __restrict__ s, int rows, int cols, int ld_src,
+                                      bf16* __restrict__ d, int ld_dst, int dst_cols) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)rows * dst_cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int r = i / dst_cols, c = i % dst_cols;
+    d[(size_t)r * ld_dst + c] = __float2bfloat16(c < cols ? s[(size_t)r * ld_src + c] : 0.f);
+  }
+}
+void launch_f32_to_bf16_2d(const float* src, int rows, int cols, int ld_src, bf16* dst, int ld_dst, int dst_cols,
+                           cudaStream_t st) {
+  const size_t n = (size_t)rows * dst_cols;
+  if (n == 0) return;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_2d_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst, dst_cols);
+}
+
+}  // namespace vv

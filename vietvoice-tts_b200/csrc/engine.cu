@@ -1,0 +1,1237 @@
+// Engine + batch state behind the C ABI (include/vvb200.h): weight loading, device layouts, the preprocess ->
+// (nfe-1) x DiT step -> decode schedule, CUDA-graph capture of the sampling loop.
+//
+// Host-side counterpart of ModelSessionManager's three sessions and TTSEngine's per-chunk loop
+// (/root/reference/vietvoicetts/core/model.py:65-135, /root/reference/vietvoicetts/core/tts_engine.py:225-238).
+#include "../../include/vvb200.h"
+#include "frontend.h"
+#include "kernels.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace vv;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(VV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CKL()                                                                                        \
+  do {                                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(VV_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ structs
+struct WTensor {
+  float* d = nullptr;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int ndim = 0;
+  size_t numel = 0;
+};
+
+struct ModTable {
+  int nfe = 0, steps = 0;
+  float* blocks = nullptr;  // [steps][depth][6*dim]
+  float* fin = nullptr;     // [steps][2*dim]
+  std::vector<float> dt;    // [steps]
+};
+
+struct GemmOp {
+  CUtensorMap tA, tB;
+  GemmShape s;
+  int bn = 128;
+};
+
+struct LayerW {
+  bf16 *qkv, *out, *ff1, *ff2;
+  const float *qkv_b, *out_b, *ff1_b, *ff2_b;
+};
+struct ConvNextW {
+  const float *dw_w, *dw_b, *ln_g, *ln_b, *pw1_b, *pw2_b, *grn_g, *grn_b, *gamma;
+  bf16 *pw1, *pw2;
+};
+
+struct vv_engine {
+  vv_arch a;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  bool finalized = false;
+  std::map<std::string, WTensor> w;
+  std::vector<void*> allocs;
+  int64_t launches = 0;
+  // tables
+  float2* rope_cs = nullptr;
+  int rope_max = 4096;
+  float2* fft_tw = nullptr;
+  float* hann = nullptr;
+  float* pos_table = nullptr;
+  std::map<int, ModTable> mod;
+  // bf16 weights
+  bf16 *in_n = nullptr, *in_c = nullptr, *c1 = nullptr, *c2 = nullptr, *out_w = nullptr;
+  int Kn = 128, Kc = 0, Kemb = 0;
+  std::vector<LayerW> layers;
+  std::vector<ConvNextW> text_blocks, voc_blocks;
+  bf16 *voc_embed = nullptr, *voc_head = nullptr;
+  // cached batches for vv_synthesize_batch
+  std::map<std::vector<int64_t>, vv_batch*> batch_cache;
+};
+
+struct vv_batch {
+  vv_engine* e = nullptr;
+  int B = 0;
+  std::vector<int> T, ref_len;
+  std::vector<int> seq_off, seq_len;  // 2B sequences (cond then uncond)
+  int R = 0, M = 0, maxT = 0;
+  std::vector<void*> allocs;
+  std::vector<bool> prepped;
+  bool committed = false, decoded = false;
+  int steps_done = 0;
+  // device index arrays
+  int32_t *seq_off_d = nullptr, *seq_len_d = nullptr, *row_pos_d = nullptr, *row_len_d = nullptr, *row_seq_d = nullptr;
+  uint8_t* row_mask_d = nullptr;
+  int32_t *tile_seq_d = nullptr, *tile_q0_d = nullptr;
+  int n_tiles = 0;
+  int32_t* ids_d = nullptr;
+  // DiT buffers
+  float *noise = nullptr, *mel = nullptr, *cond_proj = nullptr, *x = nullptr, *x0 = nullptr, *v = nullptr,
+        *cat_f32 = nullptr;
+  bf16 *noise_b = nullptr, *cat_b = nullptr, *x0b = nullptr, *h1b = nullptr, *hb = nullptr, *qkv = nullptr,
+       *attn_o = nullptr, *ffb = nullptr;
+  // text buffers
+  float *tx = nullptr, *t_tmp = nullptr, *t_ff = nullptr, *gx2 = nullptr, *nx = nullptr;
+  bf16 *t_hb = nullptr, *t_ffb = nullptr;
+  // decode buffers
+  int Rd_max = 0, Rd = 0;
+  std::vector<int> dec_off, dec_len;
+  std::vector<int64_t> pcm_off, pcm_len;
+  int32_t *d_src_row = nullptr, *d_row_pos = nullptr, *d_row_len = nullptr;
+  bf16 *v_emb = nullptr, *v_hb = nullptr, *v_ffb = nullptr;
+  float *vx = nullptr, *v_tmp = nullptr, *v_head = nullptr, *frames = nullptr;
+  int ld_head = 0;
+  int16_t* pcm_d = nullptr;
+  int64_t pcm_total = 0;
+  float* scale_tmp = nullptr;
+  std::vector<int16_t*> audio_d;
+  std::vector<int64_t> audio_cap;
+  // ops
+  GemmOp op_in, op_cond, op_c1, op_c2, op_fin;
+  std::vector<GemmOp> op_qkv, op_out, op_ff1, op_ff2, op_tpw1, op_tpw2, op_vpw1, op_vpw2;
+  GemmOp op_vemb, op_vhead;
+  CUtensorMap tQKV;
+  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, int64_t> graph_launches;
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+template <typename T>
+static int dev_alloc(std::vector<void*>& list, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  CK(cudaMalloc(&p, bytes));
+  if (zero) CK(cudaMemset(p, 0, bytes));
+  list.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+#define TRY(x)            \
+  do {                    \
+    int _r = (x);         \
+    if (_r != 0) return _r; \
+  } while (0)
+
+static const WTensor* find_w(const vv_engine* e, const std::string& n) {
+  auto it = e->w.find(n);
+  return it == e->w.end() ? nullptr : &it->second;
+}
+static int need_w(const vv_engine* e, const std::string& n, const float** out, size_t numel) {
+  const WTensor* t = find_w(e, n);
+  if (!t) return fail(VV_ERR_FORMAT, "weight tensor '%s' missing from loaded blobs", n.c_str());
+  if (numel && t->numel != numel)
+    return fail(VV_ERR_FORMAT, "weight tensor '%s' has %zu elements, expected %zu", n.c_str(), t->numel, numel);
+  *out = t->d;
+  return 0;
+}
+
+static int pick_bn(int M, int N, int sms) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const long mt = (M + 127) / 128;
+  const long t128 = mt * ((N + 127) / 128), t256 = mt * ((N + 255) / 256);
+  const double c128 = (double)((t128 + sms - 1) / sms) * 1.0;
+  const double c256 = (double)((t256 + sms - 1) / sms) * 2.0 * 0.85;
+  return c256 <= c128 ? 256 : 128;
+}
+
+static GemmOp make_op(vv_engine* e, const bf16* A, int lda, int a_rows, int M, const bf16* Bw, int ldb, int N, int K) {
+  GemmOp op;
+  op.s.M = M; op.s.N = N; op.s.K = K;
+  op.bn = pick_bn(M, N, e->num_sms);
+  op.tA = make_tmap_bf16(A, a_rows, K, lda, 128);
+  op.tB = make_tmap_bf16(Bw, N, K, ldb, op.bn);
+  return op;
+}
+static GemmOp make_conv_op(vv_engine* e, const bf16* X, int ldx, int a_rows, int M, const bf16* Wt, int groups, int taps) {
+  GemmOp op;
+  op.s.M = M; op.s.N = groups * 64; op.s.K = taps * 64;
+  op.s.conv_taps = taps; op.s.conv_groups = groups;
+  op.bn = 64;
+  op.tA = make_tmap_bf16(X, a_rows, groups * 64, ldx, 128);
+  op.tB = make_tmap_bf16(Wt, (uint64_t)groups * taps * 64, 64, 64, 64);
+  return op;
+}
+static inline void run_gemm(vv_engine* e, const GemmOp& op, const GemmEpi& epi) {
+  launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st);
+  e->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI: misc
+extern "C" const char* vv_last_error(void) { return g_err.c_str(); }
+extern "C" int vv_version(void) { return 100; }
+extern "C" int vv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int arch_check(const vv_arch& a) {
+  if (a.heads * a.head_dim != a.dim || a.head_dim != 64) return fail(VV_ERR_ARG, "arch: need head_dim 64 and heads*64 == dim");
+  if (a.dim / a.conv_pos_groups != 64) return fail(VV_ERR_ARG, "arch: conv_pos needs 64 channels per group");
+  if (a.n_fft != 1024 || a.hop != 256) return fail(VV_ERR_ARG, "arch: mel/iSTFT kernels need n_fft 1024, hop 256");
+  const int dims[] = {a.dim, a.ff_dim, a.text_dim, a.text_ff, a.voc_dim, a.voc_ff};
+  for (int d : dims)
+    if (d % 64) return fail(VV_ERR_ARG, "arch: layer widths must be multiples of 64");
+  const int lnd[] = {a.dim, a.text_dim, a.voc_dim};
+  for (int d : lnd)
+    if (d % 128 || d > 2048) return fail(VV_ERR_ARG, "arch: LayerNorm widths must be multiples of 128, <= 2048");
+  if (a.n_mel > 128 || a.rope_heads < 0 || a.rope_heads > a.heads || a.nfe < 2) return fail(VV_ERR_ARG, "arch: bad n_mel/rope_heads/nfe");
+  return 0;
+}
+
+static int build_tables(vv_engine* e) {
+  const vv_arch& a = e->a;
+  // ---- tables (host double -> float, as the oracle does)
+  {
+    std::vector<float2> cs((size_t)e->rope_max * 32);
+    for (int p = 0; p < e->rope_max; ++p)
+      for (int k = 0; k < 32; ++k) {
+        const double inv = 1.0 / pow((double)a.rope_theta, (double)(2 * k) / (double)a.head_dim);
+        cs[(size_t)p * 32 + k] = make_float2((float)cos(p * inv), (float)sin(p * inv));
+      }
+    TRY(dev_alloc(e->allocs, &e->rope_cs, cs.size()));
+    CK(cudaMemcpy(e->rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    std::vector<float2> tw(512);
+    for (int k = 0; k < 512; ++k) tw[k] = make_float2((float)cos(-2.0 * M_PI * k / 1024.0), (float)sin(-2.0 * M_PI * k / 1024.0));
+    TRY(dev_alloc(e->allocs, &e->fft_tw, tw.size()));
+    CK(cudaMemcpy(e->fft_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    std::vector<float> hn(1024);
+    for (int n = 0; n < 1024; ++n) hn[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / 1024.0));
+    TRY(dev_alloc(e->allocs, &e->hann, hn.size()));
+    CK(cudaMemcpy(e->hann, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice));
+    const int td = a.text_dim, hd = td / 2;
+    std::vector<float> pt((size_t)a.pos_table_len * td);
+    for (int p = 0; p < a.pos_table_len; ++p)
+      for (int k = 0; k < hd; ++k) {
+        const double f = 1.0 / pow(10000.0, (double)(2 * k) / (double)td);
+        pt[(size_t)p * td + k] = (float)cos(p * f);
+        pt[(size_t)p * td + hd + k] = (float)sin(p * f);
+      }
+    TRY(dev_alloc(e->allocs, &e->pos_table, pt.size()));
+    CK(cudaMemcpy(e->pos_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int vv_engine_create(const vv_arch* arch, int device, void* stream, vv_engine** out) {
+  if (!arch || !out) return fail(VV_ERR_ARG, "vv_engine_create: null argument");
+  TRY(arch_check(*arch));
+  int n = vv_device_count();
+  if (n <= 0) return fail(VV_ERR_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(VV_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(VV_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  vv_engine* e = new vv_engine();
+  e->a = *arch;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  if (stream) {
+    e->st = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    cudaError_t r = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
+    if (r != cudaSuccess) {
+      delete e;
+      return fail(VV_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(r));
+    }
+    e->own_stream = true;
+  }
+  {
+    int r = build_tables(e);
+    if (r) {
+      vv_engine_destroy(e);
+      return r;
+    }
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" void vv_engine_destroy(vv_engine* e);
+extern "C" void* vv_engine_stream(const vv_engine* e) { return e ? (void*)e->st : nullptr; }
+extern "C" int64_t vv_engine_launch_count(const vv_engine* e) { return e ? e->launches : 0; }
+extern "C" int vv_sync(vv_engine* e) {
+  if (!e) return fail(VV_ERR_ARG, "null engine");
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+struct BlobEntry {
+  char name[96];
+  uint32_t dtype, ndim;
+  int64_t shape[4];
+  uint64_t offset, nbytes;
+};
+static_assert(sizeof(BlobEntry) == 152, "blob entry layout");
+
+extern "C" int vv_engine_load_blob(vv_engine* e, const void* blob, size_t nbytes) {
+  if (!e || !blob) return fail(VV_ERR_ARG, "vv_engine_load_blob: null argument");
+  if (e->finalized) return fail(VV_ERR_STATE, "engine already finalized");
+  const uint8_t* p = static_cast<const uint8_t*>(blob);
+  if (nbytes < 256 || memcmp(p, "VVB200W1", 8) != 0) return fail(VV_ERR_FORMAT, "not a VVB200 weight blob (bad magic)");
+  uint32_t n;
+  memcpy(&n, p + 8, 4);
+  vv_arch ba;
+  memcpy(&ba, p + 16, sizeof(vv_arch));
+  if (memcmp(&ba, &e->a, sizeof(vv_arch)) != 0) return fail(VV_ERR_FORMAT, "blob architecture differs from the engine's");
+  if (256 + (size_t)n * sizeof(BlobEntry) > nbytes) return fail(VV_ERR_FORMAT, "blob truncated (entry table)");
+  CK(cudaSetDevice(e->device));
+  for (uint32_t i = 0; i < n; ++i) {
+    BlobEntry en;
+    memcpy(&en, p + 256 + (size_t)i * sizeof(BlobEntry), sizeof(BlobEntry));
+    en.name[95] = 0;
+    if (en.dtype != 0 || en.ndim > 4 || en.offset + en.nbytes > nbytes || (en.nbytes & 3))
+      return fail(VV_ERR_FORMAT, "blob entry '%s' malformed", en.name);
+    WTensor t;
+    t.ndim = en.ndim;
+    t.numel = en.nbytes / 4;
+    for (int k = 0; k < 4; ++k) t.shape[k] = en.shape[k];
+    TRY(dev_alloc(e->allocs, &t.d, t.numel, false));
+    CK(cudaMemcpy(t.d, p + en.offset, en.nbytes, cudaMemcpyHostToDevice));
+    e->w[en.name] = t;
+  }
+  return 0;
+}
+
+// fp32 [rows, cols] (row stride ld_src, starting at column col0) -> bf16 [rows, kpad] zero padded
+static int to_bf16(vv_engine* e, const float* src, int rows, int cols, int ld_src, int col0, int kpad, bf16** out) {
+  TRY(dev_alloc(e->allocs, out, (size_t)rows * kpad));
+  launch_f32_to_bf16_2d(src + col0, rows, cols, ld_src, *out, kpad, kpad, e->st);
+  e->launches++;
+  return 0;
+}
+
+static int load_convnext(vv_engine* e, const std::string& p, int d, int ff, bool grn, ConvNextW* cw, int k) {
+  const float *pw1 = nullptr, *pw2 = nullptr;
+  TRY(need_w(e, p + ".dw.w", &cw->dw_w, (size_t)d * k));
+  TRY(need_w(e, p + ".dw.b", &cw->dw_b, d));
+  TRY(need_w(e, p + ".ln.g", &cw->ln_g, d));
+  TRY(need_w(e, p + ".ln.b", &cw->ln_b, d));
+  TRY(need_w(e, p + ".pw1.w", &pw1, (size_t)ff * d));
+  TRY(need_w(e, p + ".pw1.b", &cw->pw1_b, ff));
+  TRY(need_w(e, p + ".pw2.w", &pw2, (size_t)ff * d));
+  TRY(need_w(e, p + ".pw2.b", &cw->pw2_b, d));
+  cw->grn_g = cw->grn_b = cw->gamma = nullptr;
+  if (grn) {
+    TRY(need_w(e, p + ".grn.g", &cw->grn_g, ff));
+    TRY(need_w(e, p + ".grn.b", &cw->grn_b, ff));
+  } else {
+    TRY(need_w(e, p + ".gamma", &cw->gamma, d));
+  }
+  TRY(to_bf16(e, pw1, ff, d, d, 0, d, &cw->pw1));
+  TRY(to_bf16(e, pw2, d, ff, ff, 0, ff, &cw->pw2));
+  return 0;
+}
+
+static int build_mod_table(vv_engine* e, int nfe, ModTable** out) {
+  auto it = e->mod.find(nfe);
+  if (it != e->mod.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  if (nfe < 2 || nfe > 1024) return fail(VV_ERR_ARG, "nfe %d out of range", nfe);
+  const vv_arch& a = e->a;
+  ModTable mt;
+  mt.nfe = nfe;
+  mt.steps = nfe - 1;
+  const int S = mt.steps, half = a.time_freq_dim / 2;
+  std::vector<double> t(nfe);
+  for (int i = 0; i < nfe; ++i) {
+    double ti = nfe > 1 ? (double)i / (double)(nfe - 1) : 0.0;
+    t[i] = ti + (double)a.sway * (cos(M_PI / 2.0 * ti) - 1.0 + ti);
+  }
+  mt.dt.resize(S);
+  std::vector<float> emb((size_t)S * a.time_freq_dim);
+  for (int i = 0; i < S; ++i) {
+    mt.dt[i] = (float)(t[i + 1] - t[i]);
+    for (int k = 0; k < half; ++k) {
+      const double f = exp((double)k * (-log(10000.0) / (double)(half - 1)));
+      const double ang = 1000.0 * t[i] * f;
+      emb[(size_t)i * a.time_freq_dim + k] = (float)sin(ang);
+      emb[(size_t)i * a.time_freq_dim + half + k] = (float)cos(ang);
+    }
+  }
+  float *emb_d, *h1, *st;
+  TRY(dev_alloc(e->allocs, &emb_d, emb.size()));
+  TRY(dev_alloc(e->allocs, &h1, (size_t)S * a.dim));
+  TRY(dev_alloc(e->allocs, &st, (size_t)S * a.dim));
+  TRY(dev_alloc(e->allocs, &mt.blocks, (size_t)S * a.depth * 6 * a.dim));
+  TRY(dev_alloc(e->allocs, &mt.fin, (size_t)S * 2 * a.dim));
+  CK(cudaMemcpyAsync(emb_d, emb.data(), emb.size() * 4, cudaMemcpyHostToDevice, e->st));
+  const float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  TRY(need_w(e, "dit.time.l1.w", &w1, (size_t)a.dim * a.time_freq_dim));
+  TRY(need_w(e, "dit.time.l1.b", &b1, a.dim));
+  TRY(need_w(e, "dit.time.l2.w", &w2, (size_t)a.dim * a.dim));
+  TRY(need_w(e, "dit.time.l2.b", &b2, a.dim));
+  launch_linear_f32(emb_d, w1, b1, h1, S, a.time_freq_dim, a.dim, a.dim, 1, e->st);
+  launch_linear_f32(h1, w2, b2, st, S, a.dim, a.dim, a.dim, 1, e->st);  // st = SiLU(temb)
+  e->launches += 2;
+  for (int l = 0; l < a.depth; ++l) {
+    const float *aw = nullptr, *ab = nullptr;
+    const std::string p = "dit.blocks." + std::to_string(l) + ".ada";
+    TRY(need_w(e, p + ".w", &aw, (size_t)6 * a.dim * a.dim));
+    TRY(need_w(e, p + ".b", &ab, (size_t)6 * a.dim));
+    launch_linear_f32(st, aw, ab, mt.blocks + (size_t)l * 6 * a.dim, S, a.dim, 6 * a.dim, a.depth * 6 * a.dim, 0, e->st);
+    e->launches++;
+  }
+  const float *fw = nullptr, *fb = nullptr;
+  TRY(need_w(e, "dit.final.ada.w", &fw, (size_t)2 * a.dim * a.dim));
+  TRY(need_w(e, "dit.final.ada.b", &fb, (size_t)2 * a.dim));
+  launch_linear_f32(st, fw, fb, mt.fin, S, a.dim, 2 * a.dim, 2 * a.dim, 0, e->st);
+  e->launches++;
+  CK(cudaStreamSynchronize(e->st));
+  CKL();
+  e->mod[nfe] = mt;
+  *out = &e->mod[nfe];
+  return 0;
+}
+
+extern "C" int vv_engine_finalize(vv_engine* e) {
+  if (!e) return fail(VV_ERR_ARG, "null engine");
+  if (e->finalized) return 0;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  // ---- bf16 GEMM operands
+  const int d = a.dim;
+  e->Kn = 128;
+  e->Kc = round_up(a.n_mel + a.text_dim, 64);
+  e->Kemb = round_up(a.voc_k * a.n_mel, 64);
+  const int in_dim = 2 * a.n_mel + a.text_dim;
+  const float* wp = nullptr;
+  TRY(need_w(e, "dit.in.w", &wp, (size_t)d * in_dim));
+  TRY(to_bf16(e, wp, d, a.n_mel, in_dim, 0, e->Kn, &e->in_n));
+  TRY(to_bf16(e, wp, d, a.n_mel + a.text_dim, in_dim, a.n_mel, e->Kc, &e->in_c));
+  const int cg = 64;
+  for (int c = 0; c < 2; ++c) {
+    TRY(need_w(e, c == 0 ? "dit.pos.c1.w" : "dit.pos.c2.w", &wp, (size_t)d * cg * a.conv_pos_k));
+    bf16** dst = c == 0 ? &e->c1 : &e->c2;
+    TRY(dev_alloc(e->allocs, dst, (size_t)d * cg * a.conv_pos_k));
+    launch_permute_conv_w(wp, d, cg, a.conv_pos_k, *dst, e->st);
+    e->launches++;
+  }
+  e->layers.resize(a.depth);
+  for (int l = 0; l < a.depth; ++l) {
+    const std::string p = "dit.blocks." + std::to_string(l);
+    LayerW& L = e->layers[l];
+    TRY(need_w(e, p + ".qkv.w", &wp, (size_t)3 * d * d));
+    TRY(to_bf16(e, wp, 3 * d, d, d, 0, d, &L.qkv));
+    TRY(need_w(e, p + ".out.w", &wp, (size_t)d * d));
+    TRY(to_bf16(e, wp, d, d, d, 0, d, &L.out));
+    TRY(need_w(e, p + ".ff1.w", &wp, (size_t)a.ff_dim * d));
+    TRY(to_bf16(e, wp, a.ff_dim, d, d, 0, d, &L.ff1));
+    TRY(need_w(e, p + ".ff2.w", &wp, (size_t)a.ff_dim * d));
+    TRY(to_bf16(e, wp, d, a.ff_dim, a.ff_dim, 0, a.ff_dim, &L.ff2));
+    TRY(need_w(e, p + ".qkv.b", &L.qkv_b, (size_t)3 * d));
+    TRY(need_w(e, p + ".out.b", &L.out_b, d));
+    TRY(need_w(e, p + ".ff1.b", &L.ff1_b, a.ff_dim));
+    TRY(need_w(e, p + ".ff2.b", &L.ff2_b, d));
+  }
+  TRY(need_w(e, "dit.out.w", &wp, (size_t)a.n_mel * d));
+  TRY(to_bf16(e, wp, a.n_mel, d, d, 0, d, &e->out_w));
+  e->text_blocks.resize(a.text_layers);
+  for (int i = 0; i < a.text_layers; ++i)
+    TRY(load_convnext(e, "pre.text_blocks." + std::to_string(i), a.text_dim, a.text_ff, true, &e->text_blocks[i], 7));
+  e->voc_blocks.resize(a.voc_layers);
+  for (int i = 0; i < a.voc_layers; ++i)
+    TRY(load_convnext(e, "voc.blocks." + std::to_string(i), a.voc_dim, a.voc_ff, false, &e->voc_blocks[i], a.voc_k));
+  TRY(need_w(e, "voc.embed.w", &wp, (size_t)a.voc_dim * a.n_mel * a.voc_k));
+  TRY(dev_alloc(e->allocs, &e->voc_embed, (size_t)a.voc_dim * e->Kemb));
+  launch_permute_embed_w(wp, a.voc_dim, a.n_mel, a.voc_k, e->Kemb, e->voc_embed, e->st);
+  e->launches++;
+  TRY(need_w(e, "voc.head.w", &wp, (size_t)(a.n_fft + 2) * a.voc_dim));
+  TRY(to_bf16(e, wp, a.n_fft + 2, a.voc_dim, a.voc_dim, 0, a.voc_dim, &e->voc_head));
+  // presence checks for the remaining fp32 tensors
+  const char* req[] = {"pre.mel_fb", "pre.text_embed", "dit.in.b", "dit.pos.c1.b", "dit.pos.c2.b", "dit.out.b",
+                       "voc.embed.b", "voc.norm.g", "voc.norm.b", "voc.final.g", "voc.final.b", "voc.head.b"};
+  for (const char* n : req) TRY(need_w(e, n, &wp, 0));
+  CK(cudaStreamSynchronize(e->st));
+  CKL();
+  ModTable* mt;
+  TRY(build_mod_table(e, a.nfe, &mt));
+  e->finalized = true;
+  return 0;
+}
+
+extern "C" void vv_engine_destroy(vv_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  for (auto& kv : e->batch_cache) vv_batch_destroy(kv.second);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->own_stream) cudaStreamDestroy(e->st);
+  delete e;
+}
+
+// ------------------------------------------------------------------------------------------------ batch
+extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames, vv_batch** out) {
+  if (!e || !total_frames || !out || B <= 0) return fail(VV_ERR_ARG, "vv_batch_create: bad argument");
+  if (!e->finalized) return fail(VV_ERR_STATE, "engine not finalized");
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  vv_batch* b = new vv_batch();
+  b->e = e;
+  b->B = B;
+  const int gap = 16;  // >= conv_pos_k/2 zero rows between sequences
+  if (a.conv_pos_k / 2 > gap) {
+    delete b;
+    return fail(VV_ERR_ARG, "conv_pos_k too large for the row layout");
+  }
+  b->T.resize(B);
+  b->ref_len.assign(B, 0);
+  b->prepped.assign(B, false);
+  b->seq_off.resize(2 * B);
+  b->seq_len.resize(2 * B);
+  int R = 0;
+  for (int i = 0; i < B; ++i) {
+    if (total_frames[i] < 2 || total_frames[i] > e->rope_max) {
+      delete b;
+      return fail(VV_ERR_ARG, "total_frames[%d] = %lld out of range [2, %d]", i, (long long)total_frames[i], e->rope_max);
+    }
+    b->T[i] = (int)total_frames[i];
+    b->maxT = std::max(b->maxT, b->T[i]);
+    b->seq_off[i] = R;
+    b->seq_len[i] = b->T[i];
+    R += b->T[i] + gap;
+  }
+  R = round_up(R, 8);
+  b->R = R;
+  b->M = 2 * R;
+  for (int i = 0; i < B; ++i) {
+    b->seq_off[B + i] = R + b->seq_off[i];
+    b->seq_len[B + i] = b->T[i];
+  }
+  const int M = b->M, d = a.dim;
+  std::vector<int32_t> row_pos(M, 0), row_len(M, 0), row_seq(M, -1);
+  std::vector<uint8_t> row_mask(M, 0);
+  std::vector<int32_t> tile_seq, tile_q0;
+  for (int s = 0; s < 2 * B; ++s) {
+    for (int p = 0; p < b->seq_len[s]; ++p) {
+      const int r = b->seq_off[s] + p;
+      row_pos[r] = p; row_len[r] = b->seq_len[s]; row_seq[r] = s; row_mask[r] = 1;
+    }
+    for (int q0 = 0; q0 < b->seq_len[s]; q0 += 256) {
+      tile_seq.push_back(s);
+      tile_q0.push_back(q0);
+    }
+  }
+  b->n_tiles = (int)tile_seq.size();
+  auto& AL = b->allocs;
+#define UP(dst, vec)                                                                              \
+  do {                                                                                            \
+    int _r = dev_alloc(AL, &dst, vec.size());                                                     \
+    if (_r) { vv_batch_destroy(b); return _r; }                                                   \
+    cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);             \
+  } while (0)
+#define AB(ptr, count)                                                                            \
+  do {                                                                                            \
+    int _r = dev_alloc(AL, &ptr, (size_t)(count));                                                \
+    if (_r) { vv_batch_destroy(b); return _r; }                                                   \
+  } while (0)
+  UP(b->seq_off_d, b->seq_off);
+  UP(b->seq_len_d, b->seq_len);
+  UP(b->row_pos_d, row_pos);
+  UP(b->row_len_d, row_len);
+  UP(b->row_seq_d, row_seq);
+  UP(b->row_mask_d, row_mask);
+  UP(b->tile_seq_d, tile_seq);
+  UP(b->tile_q0_d, tile_q0);
+  AB(b->ids_d, M);
+  AB(b->noise, (size_t)R * a.n_mel);
+  AB(b->mel, (size_t)R * a.n_mel);
+  AB(b->cond_proj, (size_t)M * d);
+  AB(b->x, (size_t)M * d);
+  AB(b->x0, (size_t)M * d);
+  AB(b->v, (size_t)M * 128);
+  AB(b->cat_f32, (size_t)M * e->Kc);
+  AB(b->noise_b, (size_t)M * e->Kn);
+  AB(b->cat_b, (size_t)M * e->Kc);
+  AB(b->x0b, (size_t)M * d);
+  AB(b->h1b, (size_t)M * d);
+  AB(b->hb, (size_t)M * d);
+  AB(b->qkv, (size_t)M * 3 * d);
+  AB(b->attn_o, (size_t)M * d);
+  AB(b->ffb, (size_t)M * a.ff_dim);
+  AB(b->tx, (size_t)M * a.text_dim);
+  AB(b->t_tmp, (size_t)M * a.text_dim);
+  AB(b->t_ff, (size_t)M * a.text_ff);
+  AB(b->gx2, (size_t)2 * B * a.text_ff);
+  AB(b->nx, (size_t)2 * B * a.text_ff);
+  AB(b->t_hb, (size_t)M * a.text_dim);
+  AB(b->t_ffb, (size_t)M * a.text_ff);
+  AB(b->scale_tmp, 16);
+  // decode
+  int rd = 0;
+  for (int i = 0; i < B; ++i) rd += b->T[i];
+  b->Rd_max = round_up(rd, 8);
+  b->ld_head = round_up(a.n_fft + 2, 4);
+  AB(b->d_src_row, b->Rd_max);
+  AB(b->d_row_pos, b->Rd_max);
+  AB(b->d_row_len, b->Rd_max);
+  AB(b->v_emb, (size_t)b->Rd_max * e->Kemb);
+  AB(b->v_hb, (size_t)b->Rd_max * a.voc_dim);
+  AB(b->v_ffb, (size_t)b->Rd_max * a.voc_ff);
+  AB(b->vx, (size_t)b->Rd_max * a.voc_dim);
+  AB(b->v_tmp, (size_t)b->Rd_max * a.voc_dim);
+  AB(b->v_head, (size_t)b->Rd_max * b->ld_head);
+  AB(b->frames, (size_t)b->Rd_max * 1024);
+  AB(b->pcm_d, (size_t)b->Rd_max * a.hop);
+  b->audio_d.assign(B, nullptr);
+  b->audio_cap.assign(B, 0);
+  b->dec_off.assign(B, 0);
+  b->dec_len.assign(B, 0);
+  b->pcm_off.assign(B, 0);
+  b->pcm_len.assign(B, 0);
+#undef UP
+#undef AB
+  // ---- GEMM plans
+  b->op_in = make_op(e, b->noise_b, e->Kn, M, M, e->in_n, e->Kn, d, e->Kn);
+  b->op_cond = make_op(e, b->cat_b, e->Kc, M, M, e->in_c, e->Kc, d, e->Kc);
+  b->op_c1 = make_conv_op(e, b->x0b, d, M, M, e->c1, a.conv_pos_groups, a.conv_pos_k);
+  b->op_c2 = make_conv_op(e, b->h1b, d, M, M, e->c2, a.conv_pos_groups, a.conv_pos_k);
+  b->op_fin = make_op(e, b->hb, d, M, M, e->out_w, d, a.n_mel, d);
+  for (int l = 0; l < a.depth; ++l) {
+    const LayerW& L = e->layers[l];
+    b->op_qkv.push_back(make_op(e, b->hb, d, M, M, L.qkv, d, 3 * d, d));
+    b->op_out.push_back(make_op(e, b->attn_o, d, M, M, L.out, d, d, d));
+    b->op_ff1.push_back(make_op(e, b->hb, d, M, M, L.ff1, d, a.ff_dim, d));
+    b->op_ff2.push_back(make_op(e, b->ffb, a.ff_dim, M, M, L.ff2, a.ff_dim, d, a.ff_dim));
+  }
+  for (int i = 0; i < a.text_layers; ++i) {
+    b->op_tpw1.push_back(make_op(e, b->t_hb, a.text_dim, M, M, e->text_blocks[i].pw1, a.text_dim, a.text_ff, a.text_dim));
+    b->op_tpw2.push_back(make_op(e, b->t_ffb, a.text_ff, M, M, e->text_blocks[i].pw2, a.text_ff, a.text_dim, a.text_ff));
+  }
+  b->tQKV = make_tmap_bf16(b->qkv, M, 3 * d, 3 * d, 128);
+  *out = b;
+  return 0;
+}
+
+extern "C" void vv_batch_destroy(vv_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->e->device);
+  cudaStreamSynchronize(b->e->st);
+  for (auto& g : b->graphs) cudaGraphExecDestroy(g.second);
+  for (void* p : b->allocs) cudaFree(p);
+  for (int16_t* p : b->audio_d)
+    if (p) cudaFree(p);
+  delete b;
+}
+
+extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t n_samples, const int32_t* text_ids,
+                             int64_t n_ids, const float* noise_or_null, uint64_t seed, uint64_t chunk_key,
+                             int64_t* ref_len_out) {
+  if (!b || !audio || idx < 0 || idx >= b->B || n_ids < 0 || (n_ids > 0 && !text_ids))
+    return fail(VV_ERR_ARG, "vv_preprocess: bad argument");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  if (n_samples < a.n_fft / 2 + 1) return fail(VV_ERR_ARG, "prompt audio too short (%lld samples)", (long long)n_samples);
+  CK(cudaSetDevice(e->device));
+  const int T = b->T[idx], off = b->seq_off[idx];
+  const int ref_len = (int)(n_samples / a.hop) + 1;
+  b->ref_len[idx] = ref_len;
+  if (ref_len_out) *ref_len_out = ref_len;
+  // audio
+  if (b->audio_cap[idx] < n_samples) {
+    if (b->audio_d[idx]) CK(cudaFree(b->audio_d[idx]));
+    b->audio_d[idx] = nullptr;
+    CK(cudaMalloc(&b->audio_d[idx], (size_t)n_samples * 2));
+    b->audio_cap[idx] = n_samples;
+  }
+  CK(cudaMemcpyAsync(b->audio_d[idx], audio, (size_t)n_samples * 2, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemsetAsync(b->mel + (size_t)off * a.n_mel, 0, (size_t)T * a.n_mel * 4, e->st));
+  const WTensor* fb = find_w(e, "pre.mel_fb");
+  launch_mel(b->audio_d[idx], n_samples, a.target_rms, b->scale_tmp + (idx & 15), e->hann, e->fft_tw, fb->d, a.n_mel,
+             a.mel_clamp, std::min(ref_len, T), b->mel + (size_t)off * a.n_mel, e->st);
+  e->launches += 2;
+  // text ids: +1, truncated / zero padded to T (uncond rows stay 0)
+  std::vector<int32_t> ids(T, 0);
+  for (int i = 0; i < T && i < n_ids; ++i) {
+    const int32_t v = text_ids[i] + 1;
+    if (v < 0 || v > a.vocab) return fail(VV_ERR_ARG, "text id %d out of vocabulary range", text_ids[i]);
+    ids[i] = v;
+  }
+  CK(cudaMemcpyAsync(b->ids_d + off, ids.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));  // ids vector is a stack temporary
+  // noise
+  float* nz = b->noise + (size_t)off * a.n_mel;
+  if (noise_or_null) {
+    CK(cudaMemcpyAsync(nz, noise_or_null, (size_t)T * a.n_mel * 4, cudaMemcpyHostToDevice, e->st));
+  } else {
+    launch_philox_normal(nz, (int64_t)T * a.n_mel, seed, chunk_key, e->st);
+    e->launches++;
+  }
+  launch_noise_to_bf16(nz, T, a.n_mel, b->noise_b + (size_t)off * e->Kn, b->noise_b + (size_t)(b->R + off) * e->Kn,
+                       e->Kn, e->st);
+  e->launches++;
+  CKL();
+  b->prepped[idx] = true;
+  b->committed = false;
+  b->decoded = false;
+  b->steps_done = 0;
+  return 0;
+}
+
+// text ConvNeXt-V2 over all rows, concat, conditioning projection
+static int commit(vv_batch* b) {
+  if (b->committed) return 0;
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  const int M = b->M;
+  const WTensor* emb = find_w(e, "pre.text_embed");
+  launch_text_gather(b->ids_d, b->row_pos_d, b->row_mask_d, emb->d, e->pos_table, a.pos_table_len, M, a.text_dim,
+                     b->tx, e->st);
+  e->launches++;
+  for (int i = 0; i < a.text_layers; ++i) {
+    const ConvNextW& w = e->text_blocks[i];
+    launch_dwconv_rows(b->tx, b->row_pos_d, b->row_len_d, w.dw_w, w.dw_b, M, a.text_dim, 7, b->t_tmp, e->st);
+    launch_ln_affine(b->t_tmp, M, a.text_dim, w.ln_g, w.ln_b, a.ln_eps, b->t_hb, nullptr, e->st);
+    e->launches += 2;
+    GemmEpi e1;
+    e1.bias = w.pw1_b; e1.act = ACT_GELU_ERF; e1.out_f32 = b->t_ff; e1.ld_f32 = a.text_ff;
+    run_gemm(e, b->op_tpw1[i], e1);
+    launch_grn(b->t_ff, b->seq_off_d, b->seq_len_d, b->row_seq_d, 2 * b->B, b->maxT, M, a.text_ff, w.grn_g, w.grn_b,
+               b->gx2, b->nx, b->t_ffb, e->st);
+    e->launches += 3;
+    GemmEpi e2;
+    e2.bias = w.pw2_b; e2.resid = b->tx; e2.ld_resid = a.text_dim; e2.out_f32 = b->tx; e2.ld_f32 = a.text_dim;
+    run_gemm(e, b->op_tpw2[i], e2);
+  }
+  launch_cat_cond(b->mel, b->tx, b->row_mask_d, M, b->R, a.n_mel, a.text_dim, e->Kc, b->cat_b, b->cat_f32, e->st);
+  e->launches++;
+  GemmEpi ec;
+  const float* inb = nullptr;
+  TRY(need_w(e, "dit.in.b", &inb, a.dim));
+  ec.bias = inb; ec.row_mask = b->row_mask_d; ec.out_f32 = b->cond_proj; ec.ld_f32 = a.dim;
+  run_gemm(e, b->op_cond, ec);
+  CKL();
+  b->committed = true;
+  return 0;
+}
+
+static void run_attention(vv_batch* b) {
+  vv_engine* e = b->e;
+  AttnParams p;
+  p.seq_off = b->seq_off_d; p.seq_len = b->seq_len_d; p.tile_seq = b->tile_seq_d; p.tile_q0 = b->tile_q0_d;
+  p.n_tiles = b->n_tiles; p.heads = e->a.heads; p.dim = e->a.dim; p.out = b->attn_o;
+  p.scale_log2 = (1.0f / sqrtf((float)e->a.head_dim)) * 1.4426950408889634f;
+  launch_attention(b->tQKV, p, e->st);
+  e->launches++;
+}
+
+// one DiT evaluation (both CFG branches) + Euler update.  n_layers < 0: all layers + final projection.
+static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  const int M = b->M, d = a.dim;
+  const float *c1b = nullptr, *c2b = nullptr, *outb = nullptr;
+  TRY(need_w(e, "dit.pos.c1.b", &c1b, d));
+  TRY(need_w(e, "dit.pos.c2.b", &c2b, d));
+  TRY(need_w(e, "dit.out.b", &outb, a.n_mel));
+  {  // input embedding: x0 = noise @ Wn^T + (cond @ Wc^T + b)
+    GemmEpi ep;
+    ep.resid = b->cond_proj; ep.ld_resid = d; ep.out_f32 = b->x0; ep.ld_f32 = d; ep.out_bf16 = b->x0b; ep.ld_bf16 = d;
+    run_gemm(e, b->op_in, ep);
+  }
+  {  // conv_pos_embed: x = x0 + mish(conv2(mish(conv1(x0))))
+    GemmEpi e1;
+    e1.bias = c1b; e1.act = ACT_MISH; e1.row_mask = b->row_mask_d; e1.out_bf16 = b->h1b; e1.ld_bf16 = d;
+    run_gemm(e, b->op_c1, e1);
+    GemmEpi e2;
+    e2.bias = c2b; e2.act = ACT_MISH; e2.resid = b->x0; e2.ld_resid = d; e2.row_mask = b->row_mask_d;
+    e2.out_f32 = b->x; e2.ld_f32 = d;
+    run_gemm(e, b->op_c2, e2);
+  }
+  const int L = n_layers < 0 ? a.depth : std::min(n_layers, a.depth);
+  for (int l = 0; l < L; ++l) {
+    const LayerW& W = e->layers[l];
+    const float* m = mt.blocks + ((size_t)step * a.depth + l) * 6 * d;
+    launch_ln_mod(b->x, M, d, m, m + d, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    GemmEpi eq;
+    eq.bias = W.qkv_b; eq.out_bf16 = b->qkv; eq.ld_bf16 = 3 * d;
+    eq.rope_dim = a.rope_heads * a.head_dim; eq.rope_off2 = d; eq.row_pos = b->row_pos_d; eq.rope_cs = e->rope_cs;
+    run_gemm(e, b->op_qkv[l], eq);
+    run_attention(b);
+    GemmEpi eo;
+    eo.bias = W.out_b; eo.gate = m + 2 * d; eo.resid = b->x; eo.ld_resid = d; eo.out_f32 = b->x; eo.ld_f32 = d;
+    run_gemm(e, b->op_out[l], eo);
+    launch_ln_mod(b->x, M, d, m + 3 * d, m + 4 * d, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    GemmEpi e1;
+    e1.bias = W.ff1_b; e1.act = ACT_GELU_TANH; e1.out_bf16 = b->ffb; e1.ld_bf16 = a.ff_dim;
+    run_gemm(e, b->op_ff1[l], e1);
+    GemmEpi e2;
+    e2.bias = W.ff2_b; e2.gate = m + 5 * d; e2.resid = b->x; e2.ld_resid = d; e2.out_f32 = b->x; e2.ld_f32 = d;
+    run_gemm(e, b->op_ff2[l], e2);
+  }
+  if (n_layers < 0) {
+    const float* f = mt.fin + (size_t)step * 2 * d;  // (scale, shift)
+    launch_ln_mod(b->x, M, d, f + d, f, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    GemmEpi ef;
+    ef.bias = outb; ef.out_f32 = b->v; ef.ld_f32 = 128;
+    run_gemm(e, b->op_fin, ef);
+    launch_cfg_euler(b->noise, b->noise_b, e->Kn, b->v, 128, b->row_mask_d, b->R, a.n_mel, mt.dt[step],
+                     a.cfg_strength, e->st);
+    e->launches++;
+  }
+  return 0;
+}
+
+extern "C" int vv_sample(vv_batch* b, int nfe, int first_step, int n_steps) {
+  if (!b) return fail(VV_ERR_ARG, "null batch");
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  for (int i = 0; i < b->B; ++i)
+    if (!b->prepped[i]) return fail(VV_ERR_STATE, "vv_sample: chunk %d has not been preprocessed", i);
+  if (nfe <= 0) nfe = e->a.nfe;
+  ModTable* mt;
+  TRY(build_mod_table(e, nfe, &mt));
+  if (first_step < 0 || n_steps < 0 || first_step + n_steps > mt->steps)
+    return fail(VV_ERR_ARG, "vv_sample: steps [%d, %d) outside the %d-step grid", first_step, first_step + n_steps, mt->steps);
+  TRY(commit(b));
+  b->decoded = false;
+  if (first_step == 0 && n_steps == mt->steps && n_steps > 1) {
+    auto it = b->graphs.find(nfe);
+    if (it == b->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      const int64_t before = e->launches;
+      CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
+      int rc = 0;
+      for (int s = 0; s < n_steps && rc == 0; ++s) rc = run_step(b, *mt, s, -1);
+      cudaError_t ce = cudaStreamEndCapture(e->st, &g);
+      if (rc) return rc;
+      if (ce != cudaSuccess) return fail(VV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      cudaGraphExec_t ge = nullptr;
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      b->graph_launches[nfe] = e->launches - before;
+      e->launches = before;
+      b->graphs[nfe] = ge;
+      it = b->graphs.find(nfe);
+    }
+    CK(cudaGraphLaunch(it->second, e->st));
+    e->launches += b->graph_launches[nfe];
+  } else {
+    for (int s = first_step; s < first_step + n_steps; ++s) TRY(run_step(b, *mt, s, -1));
+    CKL();
+  }
+  b->steps_done = first_step + n_steps;
+  return 0;
+}
+
+// debugging / parity aid: input embedding + the first n_layers blocks of step `step`, no Euler update
+extern "C" int vv_debug_partial_step(vv_batch* b, int nfe, int step, int n_layers) {
+  if (!b) return fail(VV_ERR_ARG, "null batch");
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  if (nfe <= 0) nfe = e->a.nfe;
+  ModTable* mt;
+  TRY(build_mod_table(e, nfe, &mt));
+  if (step < 0 || step >= mt->steps || n_layers < 0) return fail(VV_ERR_ARG, "bad step / n_layers");
+  TRY(commit(b));
+  TRY(run_step(b, *mt, step, n_layers));
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+static int decode_all(vv_batch* b) {
+  if (b->decoded) return 0;
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  std::vector<int32_t> src(b->Rd_max, 0), pos(b->Rd_max, 0), len(b->Rd_max, 0);
+  int rd = 0;
+  int64_t po = 0;
+  for (int i = 0; i < b->B; ++i) {
+    if (!b->prepped[i]) return fail(VV_ERR_STATE, "decode: chunk %d has not been preprocessed", i);
+    const int tg = std::max(0, b->T[i] - b->ref_len[i]);
+    b->dec_off[i] = rd;
+    b->dec_len[i] = tg;
+    for (int p = 0; p < tg; ++p) {
+      src[rd + p] = b->seq_off[i] + b->ref_len[i] + p;
+      pos[rd + p] = p;
+      len[rd + p] = tg;
+    }
+    rd += tg;
+    b->pcm_off[i] = po;
+    b->pcm_len[i] = tg > 1 ? (int64_t)(tg - 1) * a.hop : 0;
+    po += b->pcm_len[i];
+  }
+  b->Rd = rd;
+  b->pcm_total = po;
+  if (rd == 0) {
+    b->decoded = true;
+    return 0;
+  }
+  CK(cudaMemcpyAsync(b->d_src_row, src.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(b->d_row_pos, pos.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(b->d_row_len, len.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  const int vd = a.voc_dim;
+  const float *eb = nullptr, *ng = nullptr, *nb = nullptr, *fg = nullptr, *fbb = nullptr, *hb = nullptr;
+  TRY(need_w(e, "voc.embed.b", &eb, vd));
+  TRY(need_w(e, "voc.norm.g", &ng, vd));
+  TRY(need_w(e, "voc.norm.b", &nb, vd));
+  TRY(need_w(e, "voc.final.g", &fg, vd));
+  TRY(need_w(e, "voc.final.b", &fbb, vd));
+  TRY(need_w(e, "voc.head.b", &hb, a.n_fft + 2));
+  launch_voc_im2col(b->noise, b->d_src_row, b->d_row_pos, b->d_row_len, rd, a.n_mel, a.voc_k, e->Kemb, b->v_emb, e->st);
+  e->launches++;
+  GemmOp op = make_op(e, b->v_emb, e->Kemb, b->Rd_max, rd, e->voc_embed, e->Kemb, vd, e->Kemb);
+  GemmEpi ee;
+  ee.bias = eb; ee.out_f32 = b->vx; ee.ld_f32 = vd;
+  run_gemm(e, op, ee);
+  launch_ln_affine(b->vx, rd, vd, ng, nb, a.ln_eps, nullptr, b->vx, e->st);
+  e->launches++;
+  for (int i = 0; i < a.voc_layers; ++i) {
+    const ConvNextW& w = e->voc_blocks[i];
+    launch_dwconv_rows(b->vx, b->d_row_pos, b->d_row_len, w.dw_w, w.dw_b, rd, vd, a.voc_k, b->v_tmp, e->st);
+    launch_ln_affine(b->v_tmp, rd, vd, w.ln_g, w.ln_b, a.ln_eps, b->v_hb, nullptr, e->st);
+    e->launches += 2;
+    GemmOp o1 = make_op(e, b->v_hb, vd, b->Rd_max, rd, w.pw1, vd, a.voc_ff, vd);
+    GemmEpi e1;
+    e1.bias = w.pw1_b; e1.act = ACT_GELU_ERF; e1.out_bf16 = b->v_ffb; e1.ld_bf16 = a.voc_ff;
+    run_gemm(e, o1, e1);
+    GemmOp o2 = make_op(e, b->v_ffb, a.voc_ff, b->Rd_max, rd, w.pw2, a.voc_ff, vd, a.voc_ff);
+    GemmEpi e2;
+    e2.bias = w.pw2_b; e2.gate = w.gamma; e2.resid = b->vx; e2.ld_resid = vd; e2.out_f32 = b->vx; e2.ld_f32 = vd;
+    run_gemm(e, o2, e2);
+  }
+  launch_ln_affine(b->vx, rd, vd, fg, fbb, a.ln_eps, b->v_hb, nullptr, e->st);
+  e->launches++;
+  GemmOp oh = make_op(e, b->v_hb, vd, b->Rd_max, rd, e->voc_head, vd, a.n_fft + 2, vd);
+  GemmEpi eh;
+  eh.bias = hb; eh.out_f32 = b->v_head; eh.ld_f32 = b->ld_head;
+  run_gemm(e, oh, eh);
+  for (int i = 0; i < b->B; ++i) {
+    if (b->dec_len[i] <= 0) continue;
+    launch_istft(b->v_head + (size_t)b->dec_off[i] * b->ld_head, b->ld_head, e->hann, e->fft_tw, a.mag_clip,
+                 b->dec_len[i], b->frames + (size_t)b->dec_off[i] * 1024, a.pcm_scale, b->pcm_d + b->pcm_off[i],
+                 b->pcm_len[i], e->st);
+    e->launches += 2;
+  }
+  CKL();
+  b->decoded = true;
+  return 0;
+}
+
+extern "C" int64_t vv_batch_pcm_len(const vv_batch* b, int idx) {
+  if (!b || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "bad argument");
+  const int tg = std::max(0, b->T[idx] - b->ref_len[idx]);
+  return tg > 1 ? (int64_t)(tg - 1) * b->e->a.hop : 0;
+}
+
+extern "C" int vv_decode(vv_batch* b, int idx, int16_t* pcm_out, int64_t capacity, int64_t* n_out) {
+  if (!b || idx < 0 || idx >= b->B || !pcm_out) return fail(VV_ERR_ARG, "vv_decode: bad argument");
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  TRY(decode_all(b));
+  const int64_t n = b->pcm_len[idx];
+  if (capacity < n) return fail(VV_ERR_ARG, "vv_decode: capacity %lld < %lld samples", (long long)capacity, (long long)n);
+  if (n > 0) CK(cudaMemcpyAsync(pcm_out, b->pcm_d + b->pcm_off[idx], (size_t)n * 2, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  if (n_out) *n_out = n;
+  return 0;
+}
+
+extern "C" int vv_decode_all(vv_batch* b, int16_t* const* pcm_out, int64_t* n_out) {
+  if (!b || !pcm_out) return fail(VV_ERR_ARG, "vv_decode_all: bad argument");
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  TRY(decode_all(b));
+  for (int i = 0; i < b->B; ++i) {
+    if (b->pcm_len[i] > 0)
+      CK(cudaMemcpyAsync(pcm_out[i], b->pcm_d + b->pcm_off[i], (size_t)b->pcm_len[i] * 2, cudaMemcpyDeviceToHost, e->st));
+    if (n_out) n_out[i] = b->pcm_len[i];
+  }
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ taps
+static int copy_rows_f32(vv_engine* e, const float* src, int ld, int row0, int rows, int cols, float* out) {
+  CK(cudaMemcpy2DAsync(out, (size_t)cols * 4, src + (size_t)row0 * ld, (size_t)ld * 4, (size_t)cols * 4, rows,
+                       cudaMemcpyDeviceToHost, e->st));
+  return 0;
+}
+static int copy_rows_bf16(vv_engine* e, const bf16* src, int ld, int row0, int rows, int cols, float* out) {
+  std::vector<uint16_t> tmp((size_t)rows * cols);
+  CK(cudaMemcpy2DAsync(tmp.data(), (size_t)cols * 2, src + (size_t)row0 * ld, (size_t)ld * 2, (size_t)cols * 2, rows,
+                       cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  for (size_t i = 0; i < tmp.size(); ++i) {
+    uint32_t u = (uint32_t)tmp[i] << 16;
+    memcpy(&out[i], &u, 4);
+  }
+  return 0;
+}
+
+extern "C" int64_t vv_get_tensor(vv_batch* b, int idx, const char* name, float* out, int64_t capacity) {
+  if (!b || !name || !out || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_get_tensor: bad argument");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  const int T = b->T[idx], off = b->seq_off[idx], offu = b->seq_off[b->B + idx];
+  const std::string n(name);
+  int64_t need = 0;
+  auto two = [&](auto fn, int cols) -> int {  // [2, T, cols]: cond rows then uncond rows
+    TRY(fn(off, out));
+    TRY(fn(offu, out + (size_t)T * cols));
+    return 0;
+  };
+  if (n == "noise") {
+    need = (int64_t)T * a.n_mel;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    TRY(copy_rows_f32(e, b->noise, a.n_mel, off, T, a.n_mel, out));
+  } else if (n == "mel") {
+    const int rl = std::min(b->ref_len[idx], T);
+    need = (int64_t)rl * a.n_mel;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    TRY(copy_rows_f32(e, b->mel, a.n_mel, off, rl, a.n_mel, out));
+  } else if (n == "cat_mel_text" || n == "cat_mel_text_drop") {
+    TRY(commit(b));
+    const int cd = a.n_mel + a.text_dim;
+    need = (int64_t)T * cd;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    TRY(copy_rows_f32(e, b->cat_f32, e->Kc, n == "cat_mel_text" ? off : offu, T, cd, out));
+  } else if (n == "hidden" || n == "x0" || n == "cond_proj") {
+    need = (int64_t)2 * T * a.dim;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    const float* src = n == "hidden" ? b->x : (n == "x0" ? b->x0 : b->cond_proj);
+    TRY(two([&](int r0, float* o) { return copy_rows_f32(e, src, a.dim, r0, T, a.dim, o); }, a.dim));
+  } else if (n == "v") {
+    need = (int64_t)2 * T * a.n_mel;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    TRY(two([&](int r0, float* o) { return copy_rows_f32(e, b->v, 128, r0, T, a.n_mel, o); }, a.n_mel));
+  } else if (n == "qkv" || n == "attn" || n == "hb" || n == "h1b" || n == "ffb") {
+    const int cols = n == "qkv" ? 3 * a.dim : (n == "ffb" ? a.ff_dim : a.dim);
+    const bf16* src = n == "qkv" ? b->qkv : (n == "attn" ? b->attn_o : (n == "hb" ? b->hb : (n == "h1b" ? b->h1b : b->ffb)));
+    need = (int64_t)2 * T * cols;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    TRY(two([&](int r0, float* o) { return copy_rows_bf16(e, src, cols, r0, T, cols, o); }, cols));
+  } else if (n == "voc_head") {
+    TRY(decode_all(b));
+    const int tg = b->dec_len[idx], cols = a.n_fft + 2;
+    need = (int64_t)tg * cols;
+    if (capacity < need) return fail(VV_ERR_ARG, "capacity too small");
+    if (tg > 0) TRY(copy_rows_f32(e, b->v_head, b->ld_head, b->dec_off[idx], tg, cols, out));
+  } else {
+    return fail(VV_ERR_ARG, "vv_get_tensor: unknown tensor '%s'", name);
+  }
+  CK(cudaStreamSynchronize(e->st));
+  return need;
+}
+
+extern "C" int vv_set_noise(vv_batch* b, int idx, const float* noise) {
+  if (!b || !noise || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_set_noise: bad argument");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  const int T = b->T[idx], off = b->seq_off[idx];
+  float* nz = b->noise + (size_t)off * a.n_mel;
+  CK(cudaMemcpyAsync(nz, noise, (size_t)T * a.n_mel * 4, cudaMemcpyHostToDevice, e->st));
+  launch_noise_to_bf16(nz, T, a.n_mel, b->noise_b + (size_t)off * e->Kn, b->noise_b + (size_t)(b->R + off) * e->Kn,
+                       e->Kn, e->st);
+  e->launches++;
+  CK(cudaStreamSynchronize(e->st));
+  b->decoded = false;
+  return 0;
+}
+
+extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, const float* cat_mel_text_drop) {
+  if (!b || !cat_mel_text || !cat_mel_text_drop || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_set_cond: bad argument");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  TRY(commit(b));
+  const int T = b->T[idx], cd = a.n_mel + a.text_dim;
+  const int offs[2] = {b->seq_off[idx], b->seq_off[b->B + idx]};
+  const float* srcs[2] = {cat_mel_text, cat_mel_text_drop};
+  for (int k = 0; k < 2; ++k) {
+    float* dstf = b->cat_f32 + (size_t)offs[k] * e->Kc;
+    CK(cudaMemcpy2DAsync(dstf, (size_t)e->Kc * 4, srcs[k], (size_t)cd * 4, (size_t)cd * 4, T, cudaMemcpyHostToDevice, e->st));
+    launch_f32_to_bf16_2d(dstf, T, cd, e->Kc, b->cat_b + (size_t)offs[k] * e->Kc, e->Kc, e->Kc, e->st);
+    e->launches++;
+  }
+  GemmEpi ec;
+  const float* inb = nullptr;
+  TRY(need_w(e, "dit.in.b", &inb, a.dim));
+  ec.bias = inb; ec.row_mask = b->row_mask_d; ec.out_f32 = b->cond_proj; ec.ld_f32 = a.dim;
+  run_gemm(e, b->op_cond, ec);
+  CK(cudaStreamSynchronize(e->st));
+  CKL();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ whole path
+extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed) {
+  if (!e || !reqs || B <= 0) return fail(VV_ERR_ARG, "vv_synthesize_batch: bad argument");
+  std::vector<int64_t> key(B);
+  for (int i = 0; i < B; ++i) key[i] = reqs[i].total_frames;
+  vv_batch* b = nullptr;
+  auto it = e->batch_cache.find(key);
+  if (it != e->batch_cache.end()) {
+    b = it->second;
+  } else {
+    TRY(vv_batch_create(e, B, key.data(), &b));
+    e->batch_cache[key] = b;
+  }
+  for (int i = 0; i < B; ++i) {
+    int64_t rl;
+    TRY(vv_preprocess(b, i, reqs[i].audio, reqs[i].n_samples, reqs[i].text_ids, reqs[i].n_ids, reqs[i].noise, seed,
+                      reqs[i].chunk_key, &rl));
+  }
+  if (nfe <= 0) nfe = e->a.nfe;
+  TRY(vv_sample(b, nfe, 0, nfe - 1));
+  TRY(decode_all(b));
+  for (int i = 0; i < B; ++i) {
+    if (reqs[i].pcm_capacity < b->pcm_len[i] || (!reqs[i].pcm_out && b->pcm_len[i] > 0))
+      return fail(VV_ERR_ARG, "request %d: pcm_capacity %lld < %lld", i, (long long)reqs[i].pcm_capacity, (long long)b->pcm_len[i]);
+    if (b->pcm_len[i] > 0)
+      CK(cudaMemcpyAsync(reqs[i].pcm_out, b->pcm_d + b->pcm_off[i], (size_t)b->pcm_len[i] * 2, cudaMemcpyDeviceToHost, e->st));
+    reqs[i].n_out = b->pcm_len[i];
+  }
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel-level ABI
+static GemmEpi to_epi(vv_engine* e, const vv_gemm_epilogue* p) {
+  GemmEpi g;
+  if (!p) return g;
+  g.bias = p->bias; g.gate = p->gate; g.resid = p->resid; g.ld_resid = p->ld_resid;
+  g.out_f32 = p->out_f32; g.ld_f32 = p->ld_f32;
+  g.out_bf16 = reinterpret_cast<bf16*>(p->out_bf16); g.ld_bf16 = p->ld_bf16;
+  g.row_mask = p->row_mask; g.row_pos = p->row_pos; g.rope_cs = e->rope_cs;
+  g.rope_dim = p->rope_dim; g.rope_off2 = p->rope_off2; g.act = p->act;
+  return g;
+}
+
+extern "C" int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* Bw, int ldb, int M, int N, int K,
+                            const vv_gemm_epilogue* epi, int bn) {
+  if (!e || !A || !Bw || M <= 0 || N <= 0 || K <= 0 || (K % 64) || (lda % 8) || (ldb % 8))
+    return fail(VV_ERR_ARG, "vv_gemm_bf16: bad argument (K %% 64 == 0, ld %% 8 == 0 required)");
+  if (bn != 64 && bn != 128 && bn != 256) bn = pick_bn(M, N, e->num_sms);
+  CK(cudaSetDevice(e->device));
+  GemmOp op;
+  op.s.M = M; op.s.N = N; op.s.K = K;
+  op.bn = bn;
+  op.tA = make_tmap_bf16(A, M, K, lda, 128);
+  op.tB = make_tmap_bf16(Bw, N, K, ldb, bn);
+  run_gemm(e, op, to_epi(e, epi));
+  CKL();
+  return 0;
+}
+
+extern "C" int vv_conv_rows_bf16(vv_engine* e, const void* X, int ldx, const void* Wt, int M, int groups, int taps,
+                                 const vv_gemm_epilogue* epi) {
+  if (!e || !X || !Wt || M <= 0 || groups <= 0 || taps <= 0 || (ldx % 8)) return fail(VV_ERR_ARG, "vv_conv_rows_bf16: bad argument");
+  CK(cudaSetDevice(e->device));
+  GemmOp op = make_conv_op(e, reinterpret_cast<const bf16*>(X), ldx, M, M, reinterpret_cast<const bf16*>(Wt), groups, taps);
+  run_gemm(e, op, to_epi(e, epi));
+  CKL();
+  return 0;
+}
+
+extern "C" int vv_attention_bf16(vv_engine* e, const void* qkv, void* out, int total_rows, const int32_t* seq_off,
+                                 const int32_t* seq_len, int n_seq, int heads) {
+  if (!e || !qkv || !out || !seq_off || !seq_len || n_seq <= 0 || heads <= 0) return fail(VV_ERR_ARG, "vv_attention_bf16: bad argument");
+  CK(cudaSetDevice(e->device));
+  const int dim = heads * 64;
+  std::vector<int32_t> ts, tq;
+  for (int s = 0; s < n_seq; ++s)
+    for (int q0 = 0; q0 < seq_len[s]; q0 += 256) {
+      ts.push_back(s);
+      tq.push_back(q0);
+    }
+  std::vector<void*> tmp;
+  int32_t *so, *sl, *tsd, *tqd;
+  TRY(dev_alloc(tmp, &so, n_seq));
+  TRY(dev_alloc(tmp, &sl, n_seq));
+  TRY(dev_alloc(tmp, &tsd, ts.size()));
+  TRY(dev_alloc(tmp, &tqd, tq.size()));
+  CK(cudaMemcpy(so, seq_off, n_seq * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(sl, seq_len, n_seq * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(tsd, ts.data(), ts.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(tqd, tq.data(), tq.size() * 4, cudaMemcpyHostToDevice));
+  CUtensorMap tm = make_tmap_bf16(qkv, total_rows, 3 * dim, 3 * dim, 128);
+  AttnParams p;
+  p.seq_off = so; p.seq_len = sl; p.tile_seq = tsd; p.tile_q0 = tqd; p.n_tiles = (int)ts.size();
+  p.heads = heads; p.dim = dim; p.out = reinterpret_cast<bf16*>(out);
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  launch_attention(tm, p, e->st);
+  e->launches++;
+  cudaError_t r = cudaStreamSynchronize(e->st);
+  for (void* q : tmp) cudaFree(q);
+  if (r != cudaSuccess) return fail(VV_ERR_CUDA, "attention kernel failed: %s", cudaGetErrorString(r));
+  CKL();
+  return 0;
+}
+
+extern "C" int vv_ln_modulate(vv_engine* e, const float* x, int rows, int dim, const float* shift, const float* scale,
+                              float eps, void* out_bf16) {
+  if (!e || !x || !shift || !scale || !out_bf16 || rows <= 0 || dim % 128 || dim > 2048) return fail(VV_ERR_ARG, "vv_ln_modulate: bad argument");
+  CK(cudaSetDevice(e->device));
+  launch_ln_mod(x, rows, dim, shift, scale, eps, reinterpret_cast<bf16*>(out_bf16), e->st);
+  e->launches++;
+  CKL();
+  return 0;
+}

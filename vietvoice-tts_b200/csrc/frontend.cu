@@ -1,0 +1,389 @@
+// Preprocess-graph and decode-graph kernels that are not GEMMs: log-mel front-end (smem FFT), text embedding
+// gather, depthwise conv over rows, GRN, conditioning concat, Philox noise, Vocos im2col, iSTFT (smem inverse FFT,
+// overlap-add, int16 pack).  All are bandwidth/latency bound and < 0.2 % of the path's FLOPs.
+//
+// Replaces the non-GEMM nodes of `preprocess.onnx` and `decode.onnx`
+// (/root/reference/vietvoicetts/core/tts_engine.py:133-146, 176-187).
+#include "frontend.h"
+#include "ptx.cuh"
+
+namespace vv {
+
+// ------------------------------------------------------------------------------------------------ FFT-1024
+// radix-2 DIT on 1024 complex points in shared memory, 256 threads; input already bit-reversed.
+__device__ __forceinline__ void fft1024(float2* s, const float2* tw, bool inverse, int tid) {
+#pragma unroll 1
+  for (int len = 2, shift = 9; len <= 1024; len <<= 1, --shift) {
+    const int half = len >> 1;
+#pragma unroll
+    for (int b = tid; b < 512; b += 256) {
+      const int grp = b / half, j = b - grp * half;
+      const int i0 = grp * len + j, i1 = i0 + half;
+      float2 w = tw[j << shift];
+      if (inverse) w.y = -w.y;
+      const float2 a = s[i0], c = s[i1];
+      const float2 t = make_float2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
+      s[i0] = make_float2(a.x + t.x, a.y + t.y);
+      s[i1] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ mel front-end
+__global__ void __launch_bounds__(1024) rms_scale_kernel(const int16_t* __restrict__ audio, int64_t n,
+                                                         float target_rms, float* __restrict__ scale_out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = (float)audio[i] * (1.0f / 32768.0f);
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      const float rms = sqrtf(s / (float)n);
+      *scale_out = (rms < target_rms && rms > 0.f) ? target_rms / rms : 1.0f;
+    }
+  }
+}
+
+// one block per frame: windowed frame -> |rFFT| -> mel filterbank -> log
+__global__ void __launch_bounds__(256)
+mel_kernel(const int16_t* __restrict__ audio, int64_t n, const float* __restrict__ scale,
+           const float* __restrict__ hann, const float2* __restrict__ tw_g, const float* __restrict__ fb, int n_mel,
+           float clamp_min, int max_frames, float* __restrict__ mel_out) {
+  __shared__ float2 s[1024];
+  __shared__ float2 tw[512];
+  __shared__ float mag[520];
+  const int f = blockIdx.x;
+  if (f >= max_frames) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 512; i += 256) tw[i] = tw_g[i];
+  const float sc = *scale * (1.0f / 32768.0f);
+  for (int i = tid; i < 1024; i += 256) {
+    int64_t idx = (int64_t)f * 256 - 512 + i;
+    if (idx < 0) idx = -idx;
+    if (idx >= n) idx = 2 * (n - 1) - idx;
+    const float v = (float)audio[idx] * sc * hann[i];
+    s[__brev((unsigned)i) >> 22] = make_float2(v, 0.f);
+  }
+  __syncthreads();
+  fft1024(s, tw, false, tid);
+  for (int k = tid; k <= 512; k += 256) mag[k] = sqrtf(s[k].x * s[k].x + s[k].y * s[k].y);
+  __syncthreads();
+  if (tid < n_mel) {
+    float acc = 0.f;
+    for (int k = 0; k <= 512; ++k) acc += mag[k] * __ldg(fb + k * n_mel + tid);
+    mel_out[(size_t)f * n_mel + tid] = logf(fmaxf(acc, clamp_min));
+  }
+}
+
+void launch_mel(const int16_t* audio, int64_t n, float target_rms, float* scale_tmp, const float* hann,
+                const float2* tw, const float* fb, int n_mel, float clamp_min, int frames, float* mel_out,
+                cudaStream_t st) {
+  rms_scale_kernel<<<1, 1024, 0, st>>>(audio, n, target_rms, scale_tmp);
+  if (frames > 0) mel_kernel<<<frames, 256, 0, st>>>(audio, n, scale_tmp, hann, tw, fb, n_mel, clamp_min, frames, mel_out);
+}
+
+// ------------------------------------------------------------------------------------------------ text path
+// tx[row, :] = embed[ids[row]] + pos_table[min(pos, L-1)]  (valid rows only; others 0)
+__global__ void text_gather_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ row_pos,
+                                   const uint8_t* __restrict__ row_mask, const float* __restrict__ embed,
+                                   const float* __restrict__ pos_table, int pos_len, int rows, int td,
+                                   float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * td) return;
+  const int r = i / td, c = i - (size_t)r * td;
+  float v = 0.f;
+  if (row_mask[r]) {
+    int p = row_pos[r];
+    if (p > pos_len - 1) p = pos_len - 1;
+    v = embed[(size_t)ids[r] * td + c] + pos_table[(size_t)p * td + c];
+  }
+  out[i] = v;
+}
+void launch_text_gather(const int32_t* ids, const int32_t* row_pos, const uint8_t* row_mask, const float* embed,
+                        const float* pos_table, int pos_len, int rows, int td, float* out, cudaStream_t st) {
+  const size_t n = (size_t)rows * td;
+  if (n) text_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, row_pos, row_mask, embed, pos_table, pos_len, rows, td, out);
+}
+
+// depthwise conv over rows with per-sequence zero padding: out[r,c] = b[c] + sum_k w[c,k] * x[r+k-K/2, c]
+__global__ void dwconv_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_pos,
+                                   const int32_t* __restrict__ row_len, const float* __restrict__ w,
+                                   const float* __restrict__ b, int rows, int C, int K, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * C) return;
+  const int r = i / C, c = i - (size_t)r * C;
+  const int pos = row_pos[r], len = row_len[r];
+  float acc = b[c];
+  const int h = K / 2;
+  for (int k = 0; k < K; ++k) {
+    const int p = pos + k - h;
+    if (p >= 0 && p < len) acc += w[c * K + k] * x[(size_t)(r + k - h) * C + c];
+  }
+  out[i] = acc;
+}
+void launch_dwconv_rows(const float* x, const int32_t* row_pos, const int32_t* row_len, const float* w,
+                        const float* b, int rows, int C, int K, float* out, cudaStream_t st) {
+  const size_t n = (size_t)rows * C;
+  if (n) dwconv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, row_pos, row_len, w, b, rows, C, K, out);
+}
+
+// GRN (ConvNeXt-V2): per sequence, per channel L2 norm over TIME.
+__global__ void grn_sumsq_kernel(const float* __restrict__ h, const int32_t* __restrict__ seq_off,
+                                 const int32_t* __restrict__ seq_len, int C, int rows_per_block,
+                                 float* __restrict__ gx2) {
+  const int seq = blockIdx.z;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int len = seq_len[seq], off = seq_off[seq];
+  const int r0 = blockIdx.y * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  if (r1 > len) r1 = len;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = h[(size_t)(off + r) * C + c];
+    s += v * v;
+  }
+  if (r1 > r0) atomicAdd(gx2 + (size_t)seq * C + c, s);
+}
+__global__ void grn_norm_kernel(const float* __restrict__ gx2, int C, float* __restrict__ nx) {
+  // one block per sequence
+  __shared__ float red[32];
+  const int seq = blockIdx.x;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += sqrtf(gx2[(size_t)seq * C + c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) red[0] = s / (float)C;
+  }
+  __syncthreads();
+  const float mean = red[0];
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    nx[(size_t)seq * C + c] = sqrtf(gx2[(size_t)seq * C + c]) / (mean + 1e-6f);
+}
+__global__ void grn_apply_kernel(const float* __restrict__ h, const int32_t* __restrict__ row_seq,
+                                 const float* __restrict__ nx, const float* __restrict__ g,
+                                 const float* __restrict__ b, int rows, int C, bf16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * C) return;
+  const int r = i / C, c = i - (size_t)r * C;
+  const int seq = row_seq[r];
+  float v = 0.f;
+  if (seq >= 0) {
+    const float x = h[i];
+    v = g[c] * (x * nx[(size_t)seq * C + c]) + b[c] + x;
+  }
+  out[i] = __float2bfloat16(v);
+}
+void launch_grn(const float* h, const int32_t* seq_off, const int32_t* seq_len, const int32_t* row_seq, int n_seq,
+                int max_len, int rows, int C, const float* g, const float* b, float* gx2, float* nx, bf16* out,
+                cudaStream_t st) {
+  if (rows == 0 || n_seq == 0) return;
+  cudaMemsetAsync(gx2, 0, (size_t)n_seq * C * sizeof(float), st);
+  const int rpb = 64;
+  dim3 grid((C + 127) / 128, (max_len + rpb - 1) / rpb, n_seq);
+  grn_sumsq_kernel<<<grid, 128, 0, st>>>(h, seq_off, seq_len, C, rpb, gx2);
+  grn_norm_kernel<<<n_seq, 256, 0, st>>>(gx2, C, nx);
+  const size_t n = (size_t)rows * C;
+  grn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, row_seq, nx, g, b, rows, C, out);
+}
+
+// cat_b[row, :] = [ mel (cond rows) or 0 (uncond rows) | text | zero pad ]  -> bf16 [rows, ld]
+__global__ void cat_cond_kernel(const float* __restrict__ mel, const float* __restrict__ tx,
+                                const uint8_t* __restrict__ row_mask, int rows, int R, int n_mel, int td, int ld,
+                                bf16* __restrict__ out, float* __restrict__ out_f32) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * ld) return;
+  const int r = i / ld, c = i - (size_t)r * ld;
+  float v = 0.f;
+  if (row_mask[r]) {
+    if (c < n_mel) v = r < R ? mel[(size_t)r * n_mel + c] : 0.f;
+    else if (c < n_mel + td) v = tx[(size_t)r * td + (c - n_mel)];
+  }
+  out[i] = __float2bfloat16(v);
+  if (out_f32) out_f32[i] = v;
+}
+void launch_cat_cond(const float* mel, const float* tx, const uint8_t* row_mask, int rows, int R, int n_mel, int td,
+                     int ld, bf16* out, float* out_f32, cudaStream_t st) {
+  const size_t n = (size_t)rows * ld;
+  if (n) cat_cond_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel, tx, row_mask, rows, R, n_mel, td, ld, out, out_f32);
+}
+
+// ------------------------------------------------------------------------------------------------ Philox N(0,1)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t key) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)key, (uint32_t)(key >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  float z[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float u1 = ((float)c[2 * i] + 1.0f) * 2.3283064365386963e-10f;       // (0,1]
+    const float u2 = (float)c[2 * i + 1] * 2.3283064365386963e-10f;            // [0,1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * i] = rad * cs;
+    z[2 * i + 1] = rad * sn;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (q * 4 + i < n) out[q * 4 + i] = z[i];
+}
+void launch_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t key, cudaStream_t st) {
+  const int64_t q = (n + 3) / 4;
+  if (q) philox_normal_kernel<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(out, n, seed, key);
+}
+
+// noise fp32 [rows_u, n_mel] (one utterance) -> bf16 copies in both CFG halves of noise_b [M, ld]
+__global__ void noise_to_bf16_kernel(const float* __restrict__ noise, int rows_u, int n_mel, bf16* __restrict__ nb0,
+                                     bf16* __restrict__ nb1, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_u * n_mel) return;
+  const int r = i / n_mel, c = i - r * n_mel;
+  const bf16 v = __float2bfloat16(noise[i]);
+  nb0[(size_t)r * ld + c] = v;
+  nb1[(size_t)r * ld + c] = v;
+}
+void launch_noise_to_bf16(const float* noise, int rows_u, int n_mel, bf16* nb0, bf16* nb1, int ld, cudaStream_t st) {
+  const int n = rows_u * n_mel;
+  if (n) noise_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(noise, rows_u, n_mel, nb0, nb1, ld);
+}
+
+// ------------------------------------------------------------------------------------------------ Vocos / iSTFT
+// im2col for Conv1d(n_mel -> voc_dim, k): A[r, tap*n_mel + c] = mel[src_row[r] + tap - k/2, c] inside the sequence
+__global__ void voc_im2col_kernel(const float* __restrict__ mel, const int32_t* __restrict__ src_row,
+                                  const int32_t* __restrict__ row_pos, const int32_t* __restrict__ row_len, int rows,
+                                  int n_mel, int K, int ld, bf16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * ld) return;
+  const int r = i / ld, col = i - (size_t)r * ld;
+  float v = 0.f;
+  if (col < K * n_mel) {
+    const int tap = col / n_mel, c = col - tap * n_mel;
+    const int p = row_pos[r] + tap - K / 2;
+    if (p >= 0 && p < row_len[r]) v = mel[(size_t)(src_row[r] + tap - K / 2) * n_mel + c];
+  }
+  out[i] = __float2bfloat16(v);
+}
+void launch_voc_im2col(const float* mel, const int32_t* src_row, const int32_t* row_pos, const int32_t* row_len,
+                       int rows, int n_mel, int K, int ld, bf16* out, cudaStream_t st) {
+  const size_t n = (size_t)rows * ld;
+  if (n) voc_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel, src_row, row_pos, row_len, rows, n_mel, K, ld, out);
+}
+
+// one block per frame: head [logmag(513) | phase(513)] -> irFFT-1024 -> * hann -> frames[r, 1024]
+__global__ void __launch_bounds__(256)
+istft_frames_kernel(const float* __restrict__ head, int ld_head, const float* __restrict__ hann,
+                    const float2* __restrict__ tw_g, float mag_clip, float* __restrict__ frames) {
+  __shared__ float2 s[1024];
+  __shared__ float2 tw[512];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < 512; i += 256) tw[i] = tw_g[i];
+  const float* hr = head + (size_t)r * ld_head;
+  for (int k = tid; k <= 512; k += 256) {
+    const float mag = fminf(expf(hr[k]), mag_clip);
+    float sn, cs;
+    sincosf(hr[513 + k], &sn, &cs);
+    float2 X = make_float2(mag * cs, mag * sn);
+    if (k == 0 || k == 512) X.y = 0.f;       // irfft ignores Im of DC / Nyquist
+    s[__brev((unsigned)k) >> 22] = X;
+    if (k > 0 && k < 512) s[__brev((unsigned)(1024 - k)) >> 22] = make_float2(X.x, -X.y);
+  }
+  __syncthreads();
+  fft1024(s, tw, true, tid);
+  for (int n = tid; n < 1024; n += 256) frames[(size_t)r * 1024 + n] = s[n].x * (1.0f / 1024.0f) * hann[n];
+}
+
+// overlap-add + window-envelope normalisation + trim n_fft/2 + scale/clamp -> int16 (truncate toward zero)
+__global__ void ola_pcm_kernel(const float* __restrict__ frames, const float* __restrict__ hann, int n_frames,
+                               float pcm_scale, int16_t* __restrict__ pcm, int64_t n_out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_out) return;
+  const int64_t p = n + 512;
+  const int f_hi = (int)(p >> 8);
+  float acc = 0.f, env = 0.f;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int f = f_hi - d;
+    if (f >= 0 && f < n_frames) {
+      const int k = (int)(p - (int64_t)f * 256);
+      acc += frames[(size_t)f * 1024 + k];
+      const float w = hann[k];
+      env += w * w;
+    }
+  }
+  float v = env > 1e-11f ? acc / env : acc;
+  v = fminf(fmaxf(v * pcm_scale, -32768.f), 32767.f);
+  pcm[n] = (int16_t)v;   // float -> int conversion truncates toward zero, as numpy astype does
+}
+
+void launch_istft(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip, int n_frames,
+                  float* frames, float pcm_scale, int16_t* pcm, int64_t n_out, cudaStream_t st) {
+  if (n_frames <= 0) return;
+  istft_frames_kernel<<<n_frames, 256, 0, st>>>(head, ld_head, hann, tw, mag_clip, frames);
+  if (n_out > 0) ola_pcm_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(frames, hann, n_frames, pcm_scale, pcm, n_out);
+}
+
+// ------------------------------------------------------------------------------------------------ weight layout
+// conv_pos weight [dim, cg, taps] fp32 -> bf16 [groups][taps][co(cg)][ci(cg)]
+__global__ void permute_conv_w_kernel(const float* __restrict__ w, int dim, int cg, int taps, bf16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)dim * cg * taps) return;
+  // out index: ((g*taps + tap)*cg + co)*cg + ci
+  const int ci = i % cg;
+  size_t t = i / cg;
+  const int co = t % cg; t /= cg;
+  const int tap = t % taps;
+  const int g = t / taps;
+  out[i] = __float2bfloat16(w[((size_t)(g * cg + co) * cg + ci) * taps + tap]);
+}
+void launch_permute_conv_w(const float* w, int dim, int cg, int taps, bf16* out, cudaStream_t st) {
+  const size_t n = (size_t)dim * cg * taps;
+  permute_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, dim, cg, taps, out);
+}
+// Vocos embed weight [vd, n_mel, K] fp32 -> bf16 [vd, ld] with column tap*n_mel + c
+__global__ void permute_embed_w_kernel(const float* __restrict__ w, int vd, int n_mel, int K, int ld, bf16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)vd * ld) return;
+  const int o = i / ld, col = i - (size_t)o * ld;
+  float v = 0.f;
+  if (col < K * n_mel) {
+    const int tap = col / n_mel, c = col - tap * n_mel;
+    v = w[((size_t)o * n_mel + c) * K + tap];
+  }
+  out[i] = __float2bfloat16(v);
+}
+void launch_permute_embed_w(const float* w, int vd, int n_mel, int K, int ld, bf16* out, cudaStream_t st) {
+  const size_t n = (size_t)vd * ld;
+  permute_embed_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, vd, n_mel, K, ld, out);
+}
+
+}  // namespace vv

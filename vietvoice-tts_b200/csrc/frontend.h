@@ -1,0 +1,28 @@
+// Launchers of the non-GEMM preprocess / decode kernels (frontend.cu).
+#pragma once
+#include "kernels.h"
+
+namespace vv {
+
+void launch_mel(const int16_t* audio, int64_t n, float target_rms, float* scale_tmp, const float* hann,
+                const float2* tw, const float* fb, int n_mel, float clamp_min, int frames, float* mel_out,
+                cudaStream_t st);
+void launch_text_gather(const int32_t* ids, const int32_t* row_pos, const uint8_t* row_mask, const float* embed,
+                        const float* pos_table, int pos_len, int rows, int td, float* out, cudaStream_t st);
+void launch_dwconv_rows(const float* x, const int32_t* row_pos, const int32_t* row_len, const float* w,
+                        const float* b, int rows, int C, int K, float* out, cudaStream_t st);
+void launch_grn(const float* h, const int32_t* seq_off, const int32_t* seq_len, const int32_t* row_seq, int n_seq,
+                int max_len, int rows, int C, const float* g, const float* b, float* gx2, float* nx, bf16* out,
+                cudaStream_t st);
+void launch_cat_cond(const float* mel, const float* tx, const uint8_t* row_mask, int rows, int R, int n_mel, int td,
+                     int ld, bf16* out, float* out_f32, cudaStream_t st);
+void launch_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t key, cudaStream_t st);
+void launch_noise_to_bf16(const float* noise, int rows_u, int n_mel, bf16* nb0, bf16* nb1, int ld, cudaStream_t st);
+void launch_voc_im2col(const float* mel, const int32_t* src_row, const int32_t* row_pos, const int32_t* row_len,
+                       int rows, int n_mel, int K, int ld, bf16* out, cudaStream_t st);
+void launch_istft(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip, int n_frames,
+                  float* frames, float pcm_scale, int16_t* pcm, int64_t n_out, cudaStream_t st);
+void launch_permute_conv_w(const float* w, int dim, int cg, int taps, bf16* out, cudaStream_t st);
+void launch_permute_embed_w(const float* w, int vd, int n_mel, int K, int ld, bf16* out, cudaStream_t st);
+
+}  // namespace vv

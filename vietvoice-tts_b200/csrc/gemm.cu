@@ -1,0 +1,349 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (accumulators in TMEM,
+// double-buffered) -> tcgen05.ld epilogue with the DiT's fused element-wise work (bias, RoPE, GELU/Mish,
+// AdaLN gate, residual, row mask).  Also runs the grouped conv_pos_embed as an implicit GEMM (one k-iteration
+// per tap, activation tile re-fetched at a shifted row coordinate; TMA zero-fills the sequence padding).
+//
+// Replaces the MatMul/Gemm/Conv nodes ONNX Runtime executes inside `transformer.onnx`
+// (/root/reference/vietvoicetts/core/tts_engine.py:161-172).
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace vv {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulators
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float mish_f(float x) {
+  float ex = __expf(fminf(x, 20.0f));
+  float n = ex * (ex + 2.0f);
+  return x * __fdividef(n, n + 2.0f);
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row, int n0, const uint32_t (&raw)[32]) {
+  int nvalid = N - n0;
+  if (nvalid <= 0) return;
+  const bool full = nvalid >= 32;
+  if (!full && nvalid > 32) nvalid = 32;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+
+  if (e.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __ldg(e.bias + n0 + j);
+    }
+  }
+  if (e.rope_dim > 0) {
+    const bool in_q = n0 < e.rope_dim;
+    const bool in_k = n0 >= e.rope_off2 && n0 < e.rope_off2 + e.rope_dim;
+    if (in_q || in_k) {
+      const int pos = e.row_pos[row];
+      const float2* cs = e.rope_cs + (size_t)pos * 32 + ((n0 & 63) >> 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float2 t = __ldg(cs + i);
+        float x0 = v[2 * i], x1 = v[2 * i + 1];
+        v[2 * i] = x0 * t.x - x1 * t.y;
+        v[2 * i + 1] = x1 * t.x + x0 * t.y;
+      }
+    }
+  }
+  if (e.act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if (e.act == ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  } else if (e.act == ACT_MISH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = mish_f(v[j]);
+  }
+  if (e.gate) {
+    if (full) {
+      const float4* g4 = reinterpret_cast<const float4*>(e.gate + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 g = __ldg(g4 + j);
+        v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] *= __ldg(e.gate + n0 + j);
+    }
+  }
+  if (e.resid) {
+    const float* r = e.resid + (size_t)row * e.ld_resid + n0;
+    if (full) {
+      const float4* r4 = reinterpret_cast<const float4*>(r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = r4[j];
+        v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += r[j];
+    }
+  }
+  if (e.row_mask && e.row_mask[row] == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+  }
+  if (e.out_f32) {
+    float* o = e.out_f32 + (size_t)row * e.ld_f32 + n0;
+    if (full) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = v[j];
+    }
+  }
+  if (e.out_bf16) {
+    bf16* o = e.out_bf16 + (size_t)row * e.ld_bf16 + n0;
+    if (full) {
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        o4[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
+            const GemmEpi e) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (s.M + BM - 1) / BM;
+  const int n_tiles = CONV ? s.conv_groups : (s.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int kiters = CONV ? s.conv_taps : s.K / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < kiters; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          if (CONV) {
+            tma_load_2d(sA, &tmA, n_blk * 64, m_blk * BM + kb - s.conv_taps / 2, &full[stage]);
+            tma_load_2d(sB, &tmB, 0, (n_blk * s.conv_taps + kb) * 64, &full[stage]);
+          } else {
+            tma_load_2d(sA, &tmA, kb * BK, m_blk * BM, &full[stage]);
+            tma_load_2d(sB, &tmB, kb * BK, n_blk * BN, &full[stage]);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < kiters; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t a0 = make_sdesc_sw128(a_addr);
+          const uint64_t b0 = make_sdesc_sw128(a_addr + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_ss(d, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int w = warp - 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + w * 32 + lane;
+      const bool row_ok = row < s.M;
+      const int nbase = CONV ? n_blk * 64 : n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + (uint32_t(w * 32) << 16) + acc * BN + c * 32, raw);
+        tmem_ld_wait();
+        if (row_ok) epilogue_chunk(e, s.N, row, nbase + c * 32, raw);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+CUtensorMap make_tmap_bf16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    fprintf(stderr, "vvb200: cuTensorMapEncodeTiled entry point not available\n");
+    abort();
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "vvb200: cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u base=%p\n",
+            (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, base);
+    abort();
+  }
+  return m;
+}
+
+template <int BN, bool CONV>
+static void launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
+                     int num_sms, cudaStream_t st) {
+  using C = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    attr_set = true;
+  }
+  const int m_tiles = (s.M + BM - 1) / BM;
+  const int n_tiles = CONV ? s.conv_groups : (s.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > num_sms) grid = num_sms;
+  if (grid < 1) return;
+  gemm_kernel<BN, CONV><<<grid, 256, C::SMEM, st>>>(tmA, tmB, s, e);
+}
+
+void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
+                 int num_sms, cudaStream_t st) {
+  if (s.conv_taps > 0) {
+    launch_t<64, true>(tmA, tmB, s, e, num_sms, st);
+  } else if (bn == 256) {
+    launch_t<256, false>(tmA, tmB, s, e, num_sms, st);
+  } else if (bn == 128) {
+    launch_t<128, false>(tmA, tmB, s, e, num_sms, st);
+  } else {
+    launch_t<64, false>(tmA, tmB, s, e, num_sms, st);
+  }
+}
+
+}  // namespace vv
