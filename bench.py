@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric   : synthesized audio-seconds per second (inverse RTF), whole job over N GPUs
+workload : configs[1] — batch of 8 ~10 s utterances with CFG, NFE 32, per GPU: prompt 6.0 s (T_ref 563) + target
+           10.0 s (T_tgt 938) -> T 1501 mel frames, 270 text ids, DiT 1024/22/16 (SURVEY.md 8d cfg 2)
+step     : one pass of the hot path (preprocess -> 31 DiT evaluations with CFG + Euler -> Vocos/iSTFT decode) over
+           one batch of 8 utterances; random-init weights of the named architecture, synthetic prompt/text.
+value    : inputs resident in HBM (vv_run_resident), CUDA events on the launching stream, max over ranks
+e2e      : the same through the host-buffer C-ABI call (vv_synthesize_batch): pinned host prompt PCM + ids in,
+           int16 PCM out, copies inside the timed region
+multi-GPU: utterances are independent -> each rank runs its own batches, no data-path collective ("weak")
+
+`--impl reference` times the reference's CPU path.  ONNX Runtime and the model tarball are not installable
+offline, so that arm runs the oracle restatement (oracle/, PyTorch CPU fp32, all host threads) on a
+bounded sample of the same workload: kind "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORK = dict(B=8, prompt_samples=144000, target_seconds=10.0, n_ids=270, nfe=32)
+
+
+def workload_dims(arch):
+    t_ref = WORK["prompt_samples"] // arch.hop + 1
+    t_tgt = int(WORK["target_seconds"] * arch.sample_rate) // arch.hop + 1
+    T = t_ref + t_tgt
+    audio_s = (t_tgt - 1) * arch.hop / arch.sample_rate
+    return t_ref, t_tgt, T, audio_s
+
+
+def dit_flops(arch, T):
+    """ALGORITHMIC FLOPs of one DiT forward of one branch at T tokens."""
+    d, ff = arch.dim, arch.ff_dim
+    lin = {"qkv": 2 * d * 3 * d, "out": 2 * d * d, "ff1": 2 * d * ff, "ff2": 2 * ff * d}
+    attn = 4 * T * d
+    per_tok = {k: v * arch.depth for k, v in lin.items()}
+    per_tok["attn"] = attn * arch.depth
+    per_tok["embed"] = 2 * arch.in_dim * d + 2 * (2 * arch.conv_pos_k * (d // arch.conv_pos_groups) * d) + 2 * d * arch.n_mel
+    return {k: v * T for k, v in per_tok.items()}
+
+
+def make_inputs(arch, B, T, rank):
+    from vietvoice_tts_b200 import artifact
+    rng = np.random.default_rng(9527 + rank)
+    audios = [artifact.synthetic_prompt_pcm(WORK["prompt_samples"], 9527 + 100 * rank + i) for i in range(B)]
+    ids = [rng.integers(0, arch.vocab, size=WORK["n_ids"]).astype(np.int32) for _ in range(B)]
+    return audios, ids
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = None
+        self.p = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1405.5), d.get("bf16_tflops", 1668.6), d.get("hbm_gbs", 6542.7), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------- CPU legs
+def oracle_timing(arch, threads, n_steps):
+    """Times the oracle on ONE utterance of the workload: preprocess, n_steps transformer calls, decode.
+    Returns (t_pre, t_step_mean, t_dec, audio_s)."""
+    import torch
+    from vietvoice_tts_b200 import artifact
+    from oracle.graphs import OracleSessions
+    torch.set_num_threads(threads)
+    t_ref, t_tgt, T, audio_s = workload_dims(arch)
+    W = artifact.make_random_weights(arch, 9527)
+    S = OracleSessions(arch, W)
+    audios, ids = make_inputs(arch, 1, T, 0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        pre = S.preprocess.run(audios[0].reshape(1, 1, -1), ids[0][None], np.array([T], dtype=np.int64))
+        t_pre = time.perf_counter() - t0
+        x, ts = pre[0], np.array([0], dtype=np.int32)
+        steps = []
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            x, ts = S.transformer.run(x, *pre[1:7], ts)
+            steps.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        S.decode.run(x, pre[7])
+        t_dec = time.perf_counter() - t0
+    return t_pre, steps, t_dec, audio_s
+
+
+def run_reference(args):
+    from vietvoice_tts_b200.arch import FULL
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n = args.steps + args.warmup
+    t_pre, steps, t_dec, audio_s = oracle_timing(FULL, threads, n)
+    timed = steps[args.warmup:]
+    t_step = sum(timed) / len(timed)
+    nfe = WORK["nfe"]
+    per_utt = t_pre + (nfe - 1) * t_step + t_dec
+    value = audio_s / per_utt
+    t_ref, t_tgt, T, _ = workload_dims(FULL)
+    sample = (f"1 of the batch's 8 utterances (T={T}); each bench step = 1 of its {nfe - 1} transformer calls "
+              f"(both CFG branches); preprocess {t_pre:.2f}s and decode {t_dec:.2f}s timed once; value = "
+              f"audio_s / (pre + {nfe - 1}*step + dec)")
+    line = {
+        "impl": "reference", "metric": "synth audio-sec/sec (inverse RTF)", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch of 8 ~10 s utterances with CFG, NFE=32 (CPU leg: bounded sample)",
+                   "T": T, "nfe": nfe, "weights": "random-init F5-TTS-Base/Vocos shapes, seed 9527"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle (PyTorch CPU fp32) stand-in for the reference's ONNX Runtime CPU path, which is not installable offline",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    from vietvoice_tts_b200 import artifact
+    from vietvoice_tts_b200.arch import FULL as arch
+    from vietvoice_tts_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, nfe = WORK["B"], WORK["nfe"]
+    t_ref, t_tgt, T, audio_s = workload_dims(arch)
+    W = artifact.make_random_weights(arch, 9527)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = Engine.from_weights(arch, W, device=local, stream=stream)
+    del W
+    audios, ids = make_inputs(arch, B, T, rank)
+    batch = eng.batch([T] * B)
+    for i in range(B):
+        batch.preprocess(i, audios[i], ids[i], None, seed=9527, chunk_key=rank * B + i)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        batch.run_resident(nfe)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        batch.run_resident(nfe)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count - l0
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    ms_total = float(sum(ms_steps))
+    pcm0 = batch.decode(0)
+    assert pcm0.shape[0] == (t_tgt - 1) * arch.hop and np.abs(pcm0.astype(np.int32)).max() > 0
+
+    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region
+    pin_a = [torch.from_numpy(a.copy()).pin_memory() for a in audios]
+    pin_i = [torch.from_numpy(t.copy()).pin_memory() for t in ids]
+    pin_o = [torch.empty((t_tgt - 1) * arch.hop, dtype=torch.int16).pin_memory() for _ in range(B)]
+    a_np, i_np, o_np = [t.numpy() for t in pin_a], [t.numpy() for t in pin_i], [t.numpy() for t in pin_o]
+    keys = [rank * B + i for i in range(B)]
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.synthesize_batch(a_np, i_np, [T] * B, nfe=nfe, seed=9527, chunk_keys=keys, pcm_out=o_np)
+    barrier()
+    e2e_evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.synthesize_batch(a_np, i_np, [T] * B, nfe=nfe, seed=9527, chunk_keys=keys, pcm_out=o_np)
+        e1.record()
+        e2e_evs.append((e0, e1))
+    barrier()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e2e_evs))
+    same = all(np.array_equal(o_np[0], pcm0) for _ in range(1))     # e2e result == resident result (same seeds)
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([ms_total, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- per-kernel-class times of one step (eager, event pair around every launch) -> roofline
+    for _ in range(2):
+        cls = batch.profile_step(step=1, nfe=nfe)
+    torch.cuda.synchronize()
+    fl = dit_flops(arch, T)
+    n_br = 2 * B
+    gemm_ms = sum(cls[0:4])
+    gemm_fl = n_br * (fl["qkv"] + fl["out"] + fl["ff1"] + fl["ff2"])
+    attn_fl = n_br * fl["attn"]
+    sustained, burst, hbm, which = measured_peaks()
+    gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    attn_tf = attn_fl / (cls[4] * 1e-3) / 1e12 if cls[4] > 0 else 0.0
+    M_rows = 2 * (B * (T + 16) + 7) // 8 * 8
+    ln_bytes = (2 * arch.depth + 1) * M_rows * arch.dim * 6
+    step_fl = n_br * sum(fl.values())
+    step_ms_dev = ms_total / args.steps / (nfe - 1)
+
+    total_audio = world * B * audio_s * args.steps
+    value = total_audio / (ms_total * 1e-3)
+    e2e_value = total_audio / (e2e_ms * 1e-3)
+    h2d = sum(a.nbytes for a in a_np) + sum(t.nbytes for t in i_np)
+    d2h = sum(o.nbytes for o in o_np)
+
+    line = {
+        "metric": "synth audio-sec/sec (inverse RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch of 8 ~10 s utterances with CFG, NFE=32 per GPU",
+                   "B_per_gpu": B, "T": T, "T_ref": t_ref, "T_tgt": t_tgt, "nfe": nfe, "text_ids": WORK["n_ids"],
+                   "audio_s_per_utt": audio_s, "weights": "random-init F5-TTS-Base/Vocos shapes, seed 9527",
+                   "l2": "256 MiB flush between timed steps; working set ~2 GB >> 126 MB L2",
+                   "parallelism": f"{world} independent replicas, utterances sharded by rank, no collective"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps, "matches_resident_result": bool(same)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "vv::gemm_kernel<BN,false> (qkv/out/ffn GEMMs of the 22 DiT blocks)",
+                     "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
+                     "peak_source": f"{which} bf16_tflops_sustained", "traffic": None,
+                     "ms_per_dit_eval": gemm_ms},
+        "kernels": {
+            "gemm_qkv_ms": cls[0], "gemm_out_ms": cls[1], "gemm_ff1_ms": cls[2], "gemm_ff2_ms": cls[3],
+            "attention_ms": cls[4], "attention_tflops": attn_tf, "attention_frac_of_peak": attn_tf / sustained,
+            "ln_mod_ms": cls[5], "ln_mod_gbs": ln_bytes / (cls[5] * 1e-3) / 1e9 if cls[5] > 0 else 0.0,
+            "ln_mod_frac_of_hbm": (ln_bytes / (cls[5] * 1e-3) / 1e9) / hbm if cls[5] > 0 else 0.0,
+            "conv_pos_ms": cls[6], "other_ms": cls[7], "eager_step_ms": float(sum(cls)),
+            "graph_step_ms": step_ms_dev,
+            "whole_step_tflops": step_fl / (step_ms_dev * 1e-3) / 1e12,
+            "whole_step_frac_of_peak": step_fl / (step_ms_dev * 1e-3) / 1e12 / sustained,
+        },
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        t_pre, steps, t_dec, a_s = oracle_timing(arch, threads, 3)
+        t_step = sum(steps[1:]) / len(steps[1:])
+        per_utt = t_pre + (nfe - 1) * t_step + t_dec
+        line["cpu_baseline"] = {
+            "value": a_s / per_utt, "unit": "audio-s/s", "cores": threads, "kind": "port",
+            "sample": (f"oracle (PyTorch CPU fp32) on 1 utterance of the batch (T={T}): preprocess {t_pre:.2f}s + 3 of "
+                       f"{nfe - 1} transformer calls (mean of last 2: {t_step:.2f}s, extrapolated x{nfe - 1}) + decode "
+                       f"{t_dec:.2f}s; stand-in for ONNX Runtime CPU (not installable offline)")}
+    if rank == 0:
+        print(json.dumps(line))
+    batch.close()
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

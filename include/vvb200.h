@@ -118,6 +118,14 @@ typedef struct vv_request {
 } vv_request;
 int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed);
 
+/* Same path with every input already resident in HBM (uploaded by a previous vv_preprocess of each chunk): recomputes
+ * mel + text conditioning, restores y0, runs the (nfe-1)-step loop and the decode; PCM stays on the device
+ * (fetch with vv_decode).  No host<->device copies and no host synchronisation: this is what bench.py's `value` times. */
+int vv_run_resident(vv_batch* b, int nfe);
+/* One eager DiT step with CUDA events around every launch; ms_out[8] = milliseconds per kernel class:
+ * 0 qkv GEMM, 1 out-proj GEMM, 2 ffn-up GEMM, 3 ffn-down GEMM, 4 attention, 5 LN-modulate, 6 conv_pos, 7 rest. */
+int vv_profile_step(vv_batch* b, int nfe, int step, float* ms_out);
+
 /* ---- kernel-level entry points (device pointers; used by the parity tests and micro-benchmarks) ---------- */
 typedef struct vv_gemm_epilogue {
   const float* bias;        /* [N] or NULL                           */

@@ -87,6 +87,8 @@ def load() -> C.CDLL:
             "vv_sync": (I, [P]),
             "vv_debug_partial_step": (I, [P, I, I, I]),
             "vv_synthesize_batch": (I, [P, C.POINTER(VVRequest), I, I, U64]),
+            "vv_run_resident": (I, [P, I]),
+            "vv_profile_step": (I, [P, I, I, C.POINTER(C.c_float)]),
             "vv_gemm_bf16": (I, [P, P, I, P, I, I, I, I, C.POINTER(VVGemmEpilogue), I]),
             "vv_conv_rows_bf16": (I, [P, P, I, P, I, I, I, C.POINTER(VVGemmEpilogue)]),
             "vv_attention_bf16": (I, [P, P, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, I]),

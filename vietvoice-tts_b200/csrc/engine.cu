@@ -118,6 +118,11 @@ struct vv_batch {
   int32_t *tile_seq_d = nullptr, *tile_q0_d = nullptr;
   int n_tiles = 0;
   int32_t* ids_d = nullptr;
+  int32_t* ids_h = nullptr;             // pinned staging for the id upload
+  float* noise0 = nullptr;              // y0 as preprocessed (restored by vv_run_resident)
+  std::vector<int64_t> n_samples;
+  std::vector<int> dec_ref_len;         // ref_len snapshot the cached decode layout was built for
+  std::vector<GemmOp> dec_ops;
   // DiT buffers
   float *noise = nullptr, *mel = nullptr, *cond_proj = nullptr, *x = nullptr, *x0 = nullptr, *v = nullptr,
         *cat_f32 = nullptr;
@@ -594,6 +599,12 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   UP(b->tile_seq_d, tile_seq);
   UP(b->tile_q0_d, tile_q0);
   AB(b->ids_d, M);
+  AB(b->noise0, (size_t)R * a.n_mel);
+  if (cudaMallocHost(&b->ids_h, (size_t)R * 4) != cudaSuccess) {
+    vv_batch_destroy(b);
+    return fail(VV_ERR_CUDA, "cudaMallocHost failed");
+  }
+  b->n_samples.assign(B, 0);
   AB(b->noise, (size_t)R * a.n_mel);
   AB(b->mel, (size_t)R * a.n_mel);
   AB(b->cond_proj, (size_t)M * d);
@@ -671,7 +682,25 @@ extern "C" void vv_batch_destroy(vv_batch* b) {
   for (void* p : b->allocs) cudaFree(p);
   for (int16_t* p : b->audio_d)
     if (p) cudaFree(p);
+  if (b->ids_h) cudaFreeHost(b->ids_h);
   delete b;
+}
+
+// device part of the preprocess graph for chunk idx: log-mel of the resident prompt, y0 -> bf16 operand
+static int preprocess_device(vv_batch* b, int idx) {
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  const int T = b->T[idx], off = b->seq_off[idx];
+  CK(cudaMemsetAsync(b->mel + (size_t)off * a.n_mel, 0, (size_t)T * a.n_mel * 4, e->st));
+  const WTensor* fb = find_w(e, "pre.mel_fb");
+  launch_mel(b->audio_d[idx], b->n_samples[idx], a.target_rms, b->scale_tmp + (idx & 15), e->hann, e->fft_tw, fb->d,
+             a.n_mel, a.mel_clamp, std::min(b->ref_len[idx], T), b->mel + (size_t)off * a.n_mel, e->st);
+  e->launches += 2;
+  float* nz = b->noise + (size_t)off * a.n_mel;
+  launch_noise_to_bf16(nz, T, a.n_mel, b->noise_b + (size_t)off * e->Kn, b->noise_b + (size_t)(b->R + off) * e->Kn,
+                       e->Kn, e->st);
+  e->launches++;
+  return 0;
 }
 
 extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t n_samples, const int32_t* text_ids,
@@ -685,9 +714,12 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
   CK(cudaSetDevice(e->device));
   const int T = b->T[idx], off = b->seq_off[idx];
   const int ref_len = (int)(n_samples / a.hop) + 1;
+  // text ids: +1, truncated / zero padded to T (uncond rows stay 0); validated before any state changes
+  for (int i = 0; i < T && i < n_ids; ++i)
+    if (text_ids[i] < 0 || text_ids[i] >= a.vocab) return fail(VV_ERR_ARG, "text id %d out of vocabulary range", text_ids[i]);
   b->ref_len[idx] = ref_len;
+  b->n_samples[idx] = n_samples;
   if (ref_len_out) *ref_len_out = ref_len;
-  // audio
   if (b->audio_cap[idx] < n_samples) {
     if (b->audio_d[idx]) CK(cudaFree(b->audio_d[idx]));
     b->audio_d[idx] = nullptr;
@@ -695,21 +727,9 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
     b->audio_cap[idx] = n_samples;
   }
   CK(cudaMemcpyAsync(b->audio_d[idx], audio, (size_t)n_samples * 2, cudaMemcpyHostToDevice, e->st));
-  CK(cudaMemsetAsync(b->mel + (size_t)off * a.n_mel, 0, (size_t)T * a.n_mel * 4, e->st));
-  const WTensor* fb = find_w(e, "pre.mel_fb");
-  launch_mel(b->audio_d[idx], n_samples, a.target_rms, b->scale_tmp + (idx & 15), e->hann, e->fft_tw, fb->d, a.n_mel,
-             a.mel_clamp, std::min(ref_len, T), b->mel + (size_t)off * a.n_mel, e->st);
-  e->launches += 2;
-  // text ids: +1, truncated / zero padded to T (uncond rows stay 0)
-  std::vector<int32_t> ids(T, 0);
-  for (int i = 0; i < T && i < n_ids; ++i) {
-    const int32_t v = text_ids[i] + 1;
-    if (v < 0 || v > a.vocab) return fail(VV_ERR_ARG, "text id %d out of vocabulary range", text_ids[i]);
-    ids[i] = v;
-  }
-  CK(cudaMemcpyAsync(b->ids_d + off, ids.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->st));
-  CK(cudaStreamSynchronize(e->st));  // ids vector is a stack temporary
-  // noise
+  int32_t* stage = b->ids_h + off;
+  for (int i = 0; i < T; ++i) stage[i] = i < n_ids ? text_ids[i] + 1 : 0;
+  CK(cudaMemcpyAsync(b->ids_d + off, stage, (size_t)T * 4, cudaMemcpyHostToDevice, e->st));
   float* nz = b->noise + (size_t)off * a.n_mel;
   if (noise_or_null) {
     CK(cudaMemcpyAsync(nz, noise_or_null, (size_t)T * a.n_mel * 4, cudaMemcpyHostToDevice, e->st));
@@ -717,9 +737,8 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
     launch_philox_normal(nz, (int64_t)T * a.n_mel, seed, chunk_key, e->st);
     e->launches++;
   }
-  launch_noise_to_bf16(nz, T, a.n_mel, b->noise_b + (size_t)off * e->Kn, b->noise_b + (size_t)(b->R + off) * e->Kn,
-                       e->Kn, e->st);
-  e->launches++;
+  CK(cudaMemcpyAsync(b->noise0 + (size_t)off * a.n_mel, nz, (size_t)T * a.n_mel * 4, cudaMemcpyDeviceToDevice, e->st));
+  TRY(preprocess_device(b, idx));
   CKL();
   b->prepped[idx] = true;
   b->committed = false;
@@ -764,6 +783,8 @@ static int commit(vv_batch* b) {
   b->committed = true;
   return 0;
 }
+
+static int decode_all(vv_batch* b);
 
 static void run_attention(vv_batch* b) {
   vv_engine* e = b->e;
@@ -892,39 +913,174 @@ extern "C" int vv_debug_partial_step(vv_batch* b, int nfe, int step, int n_layer
   return 0;
 }
 
+
+// Whole path with every input already resident in HBM (prompt PCM, text ids, y0): mel -> text embed -> cond ->
+// (nfe-1) DiT steps -> Vocos/iSTFT -> int16 PCM left on the device.  No host<->device copies, no host sync.
+extern "C" int vv_run_resident(vv_batch* b, int nfe) {
+  if (!b) return fail(VV_ERR_ARG, "null batch");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  for (int i = 0; i < b->B; ++i)
+    if (!b->prepped[i]) return fail(VV_ERR_STATE, "vv_run_resident: chunk %d has not been preprocessed", i);
+  CK(cudaMemcpyAsync(b->noise, b->noise0, (size_t)b->R * a.n_mel * 4, cudaMemcpyDeviceToDevice, e->st));
+  for (int i = 0; i < b->B; ++i) TRY(preprocess_device(b, i));
+  b->committed = false;
+  b->decoded = false;
+  if (nfe <= 0) nfe = a.nfe;
+  TRY(vv_sample(b, nfe, 0, nfe - 1));
+  TRY(decode_all(b));
+  return 0;
+}
+
+// One eager DiT step with a CUDA-event pair around every launch; accumulates milliseconds per kernel class:
+// 0 qkv GEMM, 1 out-proj GEMM, 2 ffn-up GEMM, 3 ffn-down GEMM, 4 attention, 5 LN-modulate, 6 conv_pos (2 launches),
+// 7 input-embed GEMM + final projection GEMM + CFG/Euler.  The state (noise) advances by that one step.
+extern "C" int vv_profile_step(vv_batch* b, int nfe, int step, float* ms_out /* [8] */) {
+  if (!b || !ms_out) return fail(VV_ERR_ARG, "vv_profile_step: bad argument");
+  vv_engine* e = b->e;
+  const vv_arch& a = e->a;
+  CK(cudaSetDevice(e->device));
+  if (nfe <= 0) nfe = a.nfe;
+  ModTable* mt;
+  TRY(build_mod_table(e, nfe, &mt));
+  if (step < 0 || step >= mt->steps) return fail(VV_ERR_ARG, "bad step");
+  TRY(commit(b));
+  const int M = b->M, d = a.dim;
+  std::vector<cudaEvent_t> evs;
+  std::vector<int> cls;
+  auto mark = [&](int c) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, e->st);
+    evs.push_back(ev);
+    cls.push_back(c);
+  };
+  const float *c1b = nullptr, *c2b = nullptr, *outb = nullptr;
+  TRY(need_w(e, "dit.pos.c1.b", &c1b, d));
+  TRY(need_w(e, "dit.pos.c2.b", &c2b, d));
+  TRY(need_w(e, "dit.out.b", &outb, a.n_mel));
+  mark(-1);
+  {
+    GemmEpi ep;
+    ep.resid = b->cond_proj; ep.ld_resid = d; ep.out_f32 = b->x0; ep.ld_f32 = d; ep.out_bf16 = b->x0b; ep.ld_bf16 = d;
+    run_gemm(e, b->op_in, ep);
+    mark(7);
+    GemmEpi e1;
+    e1.bias = c1b; e1.act = ACT_MISH; e1.row_mask = b->row_mask_d; e1.out_bf16 = b->h1b; e1.ld_bf16 = d;
+    run_gemm(e, b->op_c1, e1);
+    GemmEpi e2;
+    e2.bias = c2b; e2.act = ACT_MISH; e2.resid = b->x0; e2.ld_resid = d; e2.row_mask = b->row_mask_d;
+    e2.out_f32 = b->x; e2.ld_f32 = d;
+    run_gemm(e, b->op_c2, e2);
+    mark(6);
+  }
+  for (int l = 0; l < a.depth; ++l) {
+    const LayerW& W = e->layers[l];
+    const float* m = mt->blocks + ((size_t)step * a.depth + l) * 6 * d;
+    launch_ln_mod(b->x, M, d, m, m + d, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    mark(5);
+    GemmEpi eq;
+    eq.bias = W.qkv_b; eq.out_bf16 = b->qkv; eq.ld_bf16 = 3 * d;
+    eq.rope_dim = a.rope_heads * a.head_dim; eq.rope_off2 = d; eq.row_pos = b->row_pos_d; eq.rope_cs = e->rope_cs;
+    run_gemm(e, b->op_qkv[l], eq);
+    mark(0);
+    run_attention(b);
+    mark(4);
+    GemmEpi eo;
+    eo.bias = W.out_b; eo.gate = m + 2 * d; eo.resid = b->x; eo.ld_resid = d; eo.out_f32 = b->x; eo.ld_f32 = d;
+    run_gemm(e, b->op_out[l], eo);
+    mark(1);
+    launch_ln_mod(b->x, M, d, m + 3 * d, m + 4 * d, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    mark(5);
+    GemmEpi e1;
+    e1.bias = W.ff1_b; e1.act = ACT_GELU_TANH; e1.out_bf16 = b->ffb; e1.ld_bf16 = a.ff_dim;
+    run_gemm(e, b->op_ff1[l], e1);
+    mark(2);
+    GemmEpi e2;
+    e2.bias = W.ff2_b; e2.gate = m + 5 * d; e2.resid = b->x; e2.ld_resid = d; e2.out_f32 = b->x; e2.ld_f32 = d;
+    run_gemm(e, b->op_ff2[l], e2);
+    mark(3);
+  }
+  {
+    const float* f = mt->fin + (size_t)step * 2 * d;
+    launch_ln_mod(b->x, M, d, f + d, f, a.ln_eps, b->hb, e->st);
+    e->launches++;
+    mark(5);
+    GemmEpi ef;
+    ef.bias = outb; ef.out_f32 = b->v; ef.ld_f32 = 128;
+    run_gemm(e, b->op_fin, ef);
+    launch_cfg_euler(b->noise, b->noise_b, e->Kn, b->v, 128, b->row_mask_d, b->R, a.n_mel, mt->dt[step],
+                     a.cfg_strength, e->st);
+    e->launches++;
+    mark(7);
+  }
+  cudaError_t r = cudaStreamSynchronize(e->st);
+  for (int i = 0; i < 8; ++i) ms_out[i] = 0.f;
+  if (r == cudaSuccess)
+    for (size_t i = 1; i < evs.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+      ms_out[cls[i]] += ms;
+    }
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  if (r != cudaSuccess) return fail(VV_ERR_CUDA, "profile step failed: %s", cudaGetErrorString(r));
+  CKL();
+  b->decoded = false;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ decode
 static int decode_all(vv_batch* b) {
   if (b->decoded) return 0;
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
-  std::vector<int32_t> src(b->Rd_max, 0), pos(b->Rd_max, 0), len(b->Rd_max, 0);
-  int rd = 0;
-  int64_t po = 0;
-  for (int i = 0; i < b->B; ++i) {
+  for (int i = 0; i < b->B; ++i)
     if (!b->prepped[i]) return fail(VV_ERR_STATE, "decode: chunk %d has not been preprocessed", i);
-    const int tg = std::max(0, b->T[i] - b->ref_len[i]);
-    b->dec_off[i] = rd;
-    b->dec_len[i] = tg;
-    for (int p = 0; p < tg; ++p) {
-      src[rd + p] = b->seq_off[i] + b->ref_len[i] + p;
-      pos[rd + p] = p;
-      len[rd + p] = tg;
+  if (b->dec_ref_len != b->ref_len) {  // (re)build the packed target-frame layout
+    std::vector<int32_t> src(b->Rd_max, 0), pos(b->Rd_max, 0), len(b->Rd_max, 0);
+    int rd0 = 0;
+    int64_t po = 0;
+    for (int i = 0; i < b->B; ++i) {
+      const int tg = std::max(0, b->T[i] - b->ref_len[i]);
+      b->dec_off[i] = rd0;
+      b->dec_len[i] = tg;
+      for (int p = 0; p < tg; ++p) {
+        src[rd0 + p] = b->seq_off[i] + b->ref_len[i] + p;
+        pos[rd0 + p] = p;
+        len[rd0 + p] = tg;
+      }
+      rd0 += tg;
+      b->pcm_off[i] = po;
+      b->pcm_len[i] = tg > 1 ? (int64_t)(tg - 1) * a.hop : 0;
+      po += b->pcm_len[i];
     }
-    rd += tg;
-    b->pcm_off[i] = po;
-    b->pcm_len[i] = tg > 1 ? (int64_t)(tg - 1) * a.hop : 0;
-    po += b->pcm_len[i];
+    b->Rd = rd0;
+    b->pcm_total = po;
+    if (rd0 > 0) {
+      CK(cudaMemcpyAsync(b->d_src_row, src.data(), (size_t)rd0 * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(b->d_row_pos, pos.data(), (size_t)rd0 * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(b->d_row_len, len.data(), (size_t)rd0 * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaStreamSynchronize(e->st));
+    }
+    b->dec_ops.clear();
+    const int vd0 = a.voc_dim;
+    b->dec_ops.push_back(make_op(e, b->v_emb, e->Kemb, b->Rd_max, std::max(rd0, 1), e->voc_embed, e->Kemb, vd0, e->Kemb));
+    for (int i = 0; i < a.voc_layers; ++i) {
+      const ConvNextW& w = e->voc_blocks[i];
+      b->dec_ops.push_back(make_op(e, b->v_hb, vd0, b->Rd_max, std::max(rd0, 1), w.pw1, vd0, a.voc_ff, vd0));
+      b->dec_ops.push_back(make_op(e, b->v_ffb, a.voc_ff, b->Rd_max, std::max(rd0, 1), w.pw2, a.voc_ff, vd0, a.voc_ff));
+    }
+    b->dec_ops.push_back(make_op(e, b->v_hb, vd0, b->Rd_max, std::max(rd0, 1), e->voc_head, vd0, a.n_fft + 2, vd0));
+    b->dec_ref_len = b->ref_len;
   }
-  b->Rd = rd;
-  b->pcm_total = po;
+  const int rd = b->Rd;
   if (rd == 0) {
     b->decoded = true;
     return 0;
   }
-  CK(cudaMemcpyAsync(b->d_src_row, src.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
-  CK(cudaMemcpyAsync(b->d_row_pos, pos.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
-  CK(cudaMemcpyAsync(b->d_row_len, len.data(), (size_t)rd * 4, cudaMemcpyHostToDevice, e->st));
-  CK(cudaStreamSynchronize(e->st));
   const int vd = a.voc_dim;
   const float *eb = nullptr, *ng = nullptr, *nb = nullptr, *fg = nullptr, *fbb = nullptr, *hb = nullptr;
   TRY(need_w(e, "voc.embed.b", &eb, vd));
@@ -935,7 +1091,7 @@ static int decode_all(vv_batch* b) {
   TRY(need_w(e, "voc.head.b", &hb, a.n_fft + 2));
   launch_voc_im2col(b->noise, b->d_src_row, b->d_row_pos, b->d_row_len, rd, a.n_mel, a.voc_k, e->Kemb, b->v_emb, e->st);
   e->launches++;
-  GemmOp op = make_op(e, b->v_emb, e->Kemb, b->Rd_max, rd, e->voc_embed, e->Kemb, vd, e->Kemb);
+  const GemmOp& op = b->dec_ops[0];
   GemmEpi ee;
   ee.bias = eb; ee.out_f32 = b->vx; ee.ld_f32 = vd;
   run_gemm(e, op, ee);
@@ -946,18 +1102,18 @@ static int decode_all(vv_batch* b) {
     launch_dwconv_rows(b->vx, b->d_row_pos, b->d_row_len, w.dw_w, w.dw_b, rd, vd, a.voc_k, b->v_tmp, e->st);
     launch_ln_affine(b->v_tmp, rd, vd, w.ln_g, w.ln_b, a.ln_eps, b->v_hb, nullptr, e->st);
     e->launches += 2;
-    GemmOp o1 = make_op(e, b->v_hb, vd, b->Rd_max, rd, w.pw1, vd, a.voc_ff, vd);
+    const GemmOp& o1 = b->dec_ops[1 + 2 * i];
     GemmEpi e1;
     e1.bias = w.pw1_b; e1.act = ACT_GELU_ERF; e1.out_bf16 = b->v_ffb; e1.ld_bf16 = a.voc_ff;
     run_gemm(e, o1, e1);
-    GemmOp o2 = make_op(e, b->v_ffb, a.voc_ff, b->Rd_max, rd, w.pw2, a.voc_ff, vd, a.voc_ff);
+    const GemmOp& o2 = b->dec_ops[2 + 2 * i];
     GemmEpi e2;
     e2.bias = w.pw2_b; e2.gate = w.gamma; e2.resid = b->vx; e2.ld_resid = vd; e2.out_f32 = b->vx; e2.ld_f32 = vd;
     run_gemm(e, o2, e2);
   }
   launch_ln_affine(b->vx, rd, vd, fg, fbb, a.ln_eps, b->v_hb, nullptr, e->st);
   e->launches++;
-  GemmOp oh = make_op(e, b->v_hb, vd, b->Rd_max, rd, e->voc_head, vd, a.n_fft + 2, vd);
+  const GemmOp& oh = b->dec_ops.back();
   GemmEpi eh;
   eh.bias = hb; eh.out_f32 = b->v_head; eh.ld_f32 = b->ld_head;
   run_gemm(e, oh, eh);

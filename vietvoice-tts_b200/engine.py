@@ -166,6 +166,15 @@ class Batch:
         n = (nfe or self.e.arch.nfe) - 1 - first_step if n_steps is None else n_steps
         _lib.check(self.lib.vv_sample(self._h, nfe, first_step, n))
 
+    def run_resident(self, nfe: int = 0) -> None:
+        """whole path on inputs already resident in HBM; asynchronous on the engine stream"""
+        _lib.check(self.lib.vv_run_resident(self._h, nfe))
+
+    def profile_step(self, step: int = 0, nfe: int = 0) -> List[float]:
+        ms = (C.c_float * 8)()
+        _lib.check(self.lib.vv_profile_step(self._h, nfe, step, ms))
+        return [float(x) for x in ms]
+
     def debug_partial_step(self, step: int, n_layers: int, nfe: int = 0) -> None:
         _lib.check(self.lib.vv_debug_partial_step(self._h, nfe, step, n_layers))
 
