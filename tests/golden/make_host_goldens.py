@@ -1,0 +1,116 @@
+"""Generates the host-side golden fixtures by RUNNING THE REFERENCE'S OWN MODULES in the build container
+(/root/reference is not available on the GPU box, so the vectors are committed next to this script).
+
+    python tests/golden/make_host_goldens.py
+
+Outputs: tests/golden/host_text.json, tests/golden/host_audio.npz
+The reference's `core` package cannot be imported as a package (core/__init__.py pulls onnxruntime), so the two
+pure-Python modules are loaded by file path; `soundfile` / `pydub` (absent offline, unused by the static methods
+exercised here) are stubbed for the import only.
+"""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference/vietvoicetts/core"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(name):
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    for stub in ("soundfile", "pydub"):
+        if stub not in sys.modules:
+            m = types.ModuleType(stub)
+            m.AudioSegment = object
+            sys.modules[stub] = m
+    tp_mod = load("text_processor")
+    ap_mod = load("audio_processor")
+
+    # ------------------------------------------------------------------ text
+    vocab_path = os.path.join(HERE, "vocab_small.txt")
+    chars = list(" .,!?abcdefghijklmnopqrstuvwxyzàáảãạăâđêôơưABCĐ0123456789'")
+    with open(vocab_path, "w", encoding="utf-8") as f:
+        f.write("\n".join(chars) + "\n")
+    tp = tp_mod.TextProcessor(vocab_path)
+    rng = np.random.default_rng(9527)
+    raw_texts = [
+        "  a;b:c(d)   efg! ",
+        "Xin chào! Tôi là trợ lý AI.\nHôm nay thế nào? 🇻🇳",
+        'Giá 5$ - 10% [ok] "quote" a—b',
+        "Xin chào Việt Nam.",
+        "",
+        "   ",
+        "dòng một\n\n  dòng hai.  \ndòng ba",
+        "a,,,,b....c;;;d",
+        "Hà Nội là thủ đô của nước Cộng hòa Xã hội chủ nghĩa Việt Nam, nằm ở phía tây bắc của vùng đồng bằng "
+        "châu thổ sông Hồng. Thành phố có lịch sử hơn một nghìn năm! Bạn đã đến đây chưa? Tôi thì rồi, nhiều lần.",
+        "This is a long sentence. This is another long sentence. And a third one.",
+        "supercalifragilisticexpialidociousandevenlongerthanthatbyfar",
+        "one two three four five six seven eight nine ten eleven twelve thirteen fourteen fifteen sixteen",
+        "Tab\there\r\nCRLF line",
+        "kết thúc bằng dấu phẩy,",
+        "ĐÂY LÀ CHỮ HOA VIỆT NAM: ỲỴỶỸÝ!",
+    ]
+    words = ["xin", "chào", "việt", "nam", "hôm", "nay", "trời", "đẹp", "quá", "tôi", "đi", "học", "a", "b.",
+             "c,", "d!", "e?", "dài_lắm_luôn_đấy_nhé", "ok", "1", "22", "333,", "rồi.", "ư", "ơi!"]
+    for _ in range(40):
+        n = int(rng.integers(1, 60))
+        raw_texts.append(" ".join(rng.choice(words, size=n)))
+    cases = []
+    for t in raw_texts:
+        cleaned = tp.clean_text(t)
+        entry = {"raw": t, "clean": cleaned,
+                 "len_default": tp.calculate_text_length(cleaned, r".,?!:"),
+                 "len_class": tp.calculate_text_length(cleaned, r"[,.]"),
+                 "ids": tp.text_to_indices([list(cleaned)]).tolist(),
+                 "chunks": {}}
+        for mc in (10, 30, 60, 135):
+            entry["chunks"][str(mc)] = tp.chunk_text(cleaned, max_chars=mc)
+        entry["chunks_raw_30"] = tp.chunk_text(t, max_chars=30)
+        cases.append(entry)
+    with open(os.path.join(HERE, "host_text.json"), "w", encoding="utf-8") as f:
+        json.dump({"vocab": chars, "cases": cases}, f, ensure_ascii=False, indent=0)
+
+    # ------------------------------------------------------------------ audio
+    AP = ap_mod.AudioProcessor
+    out = {}
+    sig = (rng.standard_normal(5000) * 3000 + 200).astype(np.float32)
+    out["norm_in"] = sig
+    out["norm_out"] = AP.normalize_to_int16(sig)
+    out["norm_zero_out"] = AP.normalize_to_int16(np.zeros(16, dtype=np.float32))
+    clip = (rng.standard_normal(3000) * 9000).astype(np.float32)
+    clip[10] = 40000.0
+    clip[11] = np.nan
+    clip[12] = np.inf
+    out["clip_in"] = clip
+    out["clip_out"] = AP.fix_clipped_audio(clip)
+    ok = (rng.standard_normal(100) * 1000).astype(np.int16)
+    out["noclip_in"] = ok
+    out["noclip_out"] = AP.fix_clipped_audio(ok)
+    waves = [(rng.standard_normal(n) * a).astype(np.int16).reshape(1, 1, -1)
+             for n, a in ((6000, 4000), (5000, 900), (2000, 50), (7000, 12000), (1000, 3000))]
+    waves[3][0, 0, 5] = 32767
+    for i, w in enumerate(waves):
+        out[f"wave{i}"] = w
+    out["xf_improved"] = AP.concatenate_with_crossfade_improved(waves, 0.1, 24000)
+    out["xf_improved_two"] = AP.concatenate_with_crossfade_improved(waves[:2], 0.1, 24000)
+    out["xf_improved_nofade"] = AP.concatenate_with_crossfade_improved(waves[:3], 0.0, 24000)
+    out["xf_improved_single"] = AP.concatenate_with_crossfade_improved(waves[:1], 0.1, 24000)
+    out["xf_plain"] = AP.concatenate_with_crossfade(waves, 0.1, 24000)
+    out["xf_plain_short"] = AP.concatenate_with_crossfade([waves[4], waves[2]], 0.1, 24000)
+    np.savez_compressed(os.path.join(HERE, "host_audio.npz"), **out)
+    print("wrote host_text.json (%d cases), host_audio.npz (%d arrays)" % (len(cases), len(out)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""Host-side mirror of the reference interface vs golden vectors produced by the reference's own modules
+(tests/golden/make_host_goldens.py).  Text normalisation, chunking and token ids must match bit-exactly
+(north_star); every int16 cast in the audio helpers truncates exactly as the reference does.  Also the reference's
+own known-answer tests for these helpers."""
+import json
+import os
+import wave
+
+import numpy as np
+import pytest
+
+from vietvoice_tts_b200.host.text_processor import TextProcessor
+from vietvoice_tts_b200.host.audio_processor import AudioProcessor
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def text_gold():
+    with open(os.path.join(G, "host_text.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def tp(tmp_path_factory, text_gold):
+    p = tmp_path_factory.mktemp("v") / "vocab.txt"
+    p.write_text("\n".join(text_gold["vocab"]) + "\n", encoding="utf-8")
+    return TextProcessor(str(p))
+
+
+def test_text_goldens_bit_exact(tp, text_gold):
+    assert len(text_gold["cases"]) >= 50
+    for c in text_gold["cases"]:
+        cleaned = tp.clean_text(c["raw"])
+        assert cleaned == c["clean"], c["raw"]
+        assert tp.calculate_text_length(cleaned, r".,?!:") == c["len_default"]
+        assert tp.calculate_text_length(cleaned, r"[,.]") == c["len_class"]
+        ids = tp.text_to_indices([list(cleaned)])
+        assert ids.dtype == np.int32 and ids.tolist() == c["ids"]
+        for mc, chunks in c["chunks"].items():
+            assert tp.chunk_text(cleaned, max_chars=int(mc)) == chunks, (c["raw"], mc)
+        assert tp.chunk_text(c["raw"], max_chars=30) == c["chunks_raw_30"]
+
+
+def test_reference_known_answers_text(tmp_path):
+    # /root/reference/tests/test_text_processor_full.py:14-35
+    p = tmp_path / "vocab.txt"
+    p.write_text("a\nb\nc\n")
+    t = TextProcessor(str(p))
+    assert t.vocab_char_map == {"a": 0, "b": 1, "c": 2} and t.vocab_size == 3
+    assert t.text_to_indices([["a", "b", "c"]]).tolist() == [[0, 1, 2]]
+    assert t.text_to_indices([["a", "z"]]).tolist() == [[0, 0]]            # unknown -> 0
+    assert t.calculate_text_length("a, b, c.", r"[,.]") == len("a, b, c.".encode()) + 3 * 3 == 17
+    assert t.calculate_text_length("a, b, c.", r".,?!:") == 8              # default pattern is a regex (Appendix B)
+    assert t.clean_text("  a;b:c(d)   efg! ") == "a,b,c,d, efg!"
+    with pytest.raises(FileNotFoundError):
+        TextProcessor(str(tmp_path / "missing.txt"))
+
+
+def test_chunk_invariants(tmp_path):
+    # /root/reference/tests/test_text_processor.py:24-136
+    p = tmp_path / "vocab.txt"
+    p.write_text("a\n")
+    t = TextProcessor(str(p))
+    assert t.chunk_text("") == [] and t.chunk_text("    ") == []
+    text = "This is a long sentence. This is another long sentence. And a third one."
+    chunks = t.chunk_text(text, max_chars=30)
+    assert chunks == ["This is a long sentence.", "This is another long sentence.", "And a third one."]
+    assert all(len(c) <= 30 for c in chunks)
+    long_word = "x" * 200
+    assert t.chunk_text(long_word, max_chars=50) == [long_word]           # a single long word is returned whole
+    words = " ".join(["word"] * 100)
+    for c in t.chunk_text(words, max_chars=40):
+        assert len(c) <= 40 and all(w == "word" for w in c.split())     # never splits inside a word
+
+
+def test_audio_goldens_bit_exact():
+    g = np.load(os.path.join(G, "host_audio.npz"))
+    out = AudioProcessor.normalize_to_int16(g["norm_in"])
+    assert out.dtype == np.int16 and np.array_equal(out, g["norm_out"]) and np.abs(out).max() <= 29491
+    assert np.array_equal(AudioProcessor.normalize_to_int16(np.zeros(16, dtype=np.float32)), g["norm_zero_out"])
+    fixed = AudioProcessor.fix_clipped_audio(g["clip_in"])
+    assert fixed.dtype == g["clip_out"].dtype and np.array_equal(fixed, g["clip_out"]) and np.abs(fixed).max() < 32767
+    same = AudioProcessor.fix_clipped_audio(g["noclip_in"])
+    assert same.dtype == g["noclip_out"].dtype and np.array_equal(same, g["noclip_out"])
+    waves = [g[f"wave{i}"] for i in range(5)]
+    for name, args in (("xf_improved", (waves, 0.1)), ("xf_improved_two", (waves[:2], 0.1)),
+                       ("xf_improved_nofade", (waves[:3], 0.0)), ("xf_improved_single", (waves[:1], 0.1))):
+        r = AudioProcessor.concatenate_with_crossfade_improved(args[0], args[1], 24000)
+        assert r.dtype == g[name].dtype and np.array_equal(r, g[name]), name
+    r = AudioProcessor.concatenate_with_crossfade(waves, 0.1, 24000)
+    assert r.dtype == g["xf_plain"].dtype and np.array_equal(r, g["xf_plain"])
+    r = AudioProcessor.concatenate_with_crossfade([waves[4], waves[2]], 0.1, 24000)
+    assert np.array_equal(r, g["xf_plain_short"])
+    # /root/reference/tests/test_audio_processor_full.py:51-61 : length = sum(len) - overlap*(k-1)
+    total = waves[0].size
+    for w in waves[1:]:
+        total += w.size - min(2400, total, w.size)
+    assert g["xf_improved"].shape[0] == total == 13200
+    assert AudioProcessor.concatenate_with_crossfade_improved([], 0.1, 24000).size == 0
+
+
+def test_wav_roundtrip_and_load(tmp_path):
+    sr = 24000
+    t = np.arange(sr) / sr
+    pcm = (np.sin(2 * np.pi * 220 * t) * 12000 + 500).astype(np.int16)
+    p = str(tmp_path / "a" / "x.wav")
+    AudioProcessor.save_audio(pcm, p, sr)                                   # WAVEX
+    with wave.open(p, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, sr, sr)
+    loaded = AudioProcessor.load_audio(p, sr)
+    assert loaded.dtype == np.int16 and loaded.shape == pcm.shape
+    assert np.array_equal(loaded, AudioProcessor.normalize_to_int16(pcm.astype(np.float32)))
+    with open(p, "rb") as f:
+        assert np.array_equal(AudioProcessor.load_audio(f.read(), sr), loaded)
+    assert AudioProcessor.load_audio(p, 12000).shape[0] == sr // 2          # resampled
+    with pytest.raises(FileNotFoundError):
+        AudioProcessor.load_audio(str(tmp_path / "none.wav"), sr)
+    with pytest.raises(ValueError):
+        AudioProcessor.save_audio(np.array([], dtype=np.int16), p, sr)
+    with pytest.raises(RuntimeError):
+        AudioProcessor.load_audio(b"\x00\x00\x00\x20ftypM4A not a wav", sr)
