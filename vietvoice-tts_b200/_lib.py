@@ -14,7 +14,7 @@ import threading
 from .arch import VVArch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvvb200.so")
+LIB_PATH = os.environ.get("VVB200_LIB") or os.path.join(_HERE, "libvvb200.so")   # override: A/B kernel experiments
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "vvb200.h")
 

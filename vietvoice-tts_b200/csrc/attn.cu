@@ -75,6 +75,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp >= 8) {
+  // producer warpgroup (TMA, MMA issue, TMEM alloc, spare): hand registers to the two softmax warpgroups
+  setmaxnreg_dec<88>();
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -160,8 +163,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         phase = nphase;
       }
     }
-  } else if (warp < 8) {
+  }
+  } else {
     // ------------------------------------------------------------------ softmax warpgroups
+    setmaxnreg_inc<208>();
     const int t = warp >> 2;                 // q tile
     const int r = threadIdx.x & 127;         // row within tile == TMEM lane
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -183,9 +188,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         for (int i = 0; i < 128; ++i)
           if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx = __uint_as_float(s[0]);
+      // 4 independent 3-input max chains instead of one 127-deep dependent chain
+      float mxa = __uint_as_float(s[0]), mxb = __uint_as_float(s[1]), mxc = __uint_as_float(s[2]),
+            mxd = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      for (int i = 4; i < 124; i += 8) {
+        mxa = fmax3(mxa, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+        mxb = fmax3(mxb, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+        mxc = fmax3(mxc, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+        mxd = fmax3(mxd, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+      }
+      mxa = fmax3(mxa, __uint_as_float(s[124]), __uint_as_float(s[125]));
+      mxb = fmax3(mxb, __uint_as_float(s[126]), __uint_as_float(s[127]));
+      float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
       mx *= p.scale_log2;
       if (j == 0) {
         m_ref = mx;
@@ -208,15 +223,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           tmem_st_wait();
         }
       }
-      float sum = 0.0f;
+      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 columns (16 bytes of bf16)
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
-          sum += e[i];
-        }
+        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
+        sum0 += e[0] + e[4];
+        sum1 += e[1] + e[5];
+        sum2 += e[2] + e[6];
+        sum3 += e[3] + e[7];
         uint4 u;
         u.x = pack_bf16(e[0], e[1]);
         u.y = pack_bf16(e[2], e[3]);
@@ -225,7 +241,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         const int atom = c >> 3, chunk = c & 7;
         *reinterpret_cast<uint4*>(prow + atom * TILE_BYTES + ((chunk ^ sw) << 4)) = u;
       }
-      l += sum;
+      l += (sum0 + sum1) + (sum2 + sum3);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[t]);

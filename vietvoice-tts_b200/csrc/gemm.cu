@@ -40,7 +40,8 @@ __device__ __forceinline__ float mish_f(float x) {
   return x * __fdividef(n, n + 2.0f);
 }
 
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row, int n0, const uint32_t (&raw)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row, int n0, const uint32_t (&raw)[32],
+                                               const float4 (&rpre)[8]) {
   int nvalid = N - n0;
   if (nvalid <= 0) return;
   const bool full = nvalid >= 32;
@@ -105,10 +106,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
   if (e.resid) {
     const float* r = e.resid + (size_t)row * e.ld_resid + n0;
     if (full) {
-      const float4* r4 = reinterpret_cast<const float4*>(r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 x = r4[j];
+        const float4 x = rpre[j];   // prefetched by the caller before the accumulator was ready
         v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
       }
     } else {
@@ -155,7 +155,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
 }
 
 template <int BN, bool CONV>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
             const GemmEpi e) {
   using C = GemmCfg<BN>;
@@ -178,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -247,23 +247,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    const int w = warp - 4;
+    // 8 epilogue warps: warp%4 selects the TMEM lane quadrant (rows), (warp-4)/4 selects the column half
+    const int w = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int CH = BN / 32;                      // 32-column chunks per tile
+    constexpr int CH_PER = CH >= 2 ? CH / 2 : 1;     // chunks per epilogue warp
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], aphase);
-      tc_fence_after();
       const int row = m_blk * BM + w * 32 + lane;
       const bool row_ok = row < s.M;
       const int nbase = CONV ? n_blk * 64 : n_blk * BN;
+      const int c0 = half * CH_PER;
+      // residual prefetch for the first chunk: independent of the accumulator, overlaps the wait for the MMA
+      float4 rnext[8];
+      const bool has_res = e.resid != nullptr && row_ok;
+      auto load_res = [&](int c, float4 (&r)[8]) {
+        const int n0 = nbase + c * 32;
+        if (has_res && n0 + 32 <= s.N) {
+          const float4* r4 = reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_resid + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = r4[j];
+        }
+      };
+      if (CH >= 2 || half == 0) load_res(c0, rnext);
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      if (CH >= 2 || half == 0) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + (uint32_t(w * 32) << 16) + acc * BN + c * 32, raw);
-        tmem_ld_wait();
-        if (row_ok) epilogue_chunk(e, s.N, row, nbase + c * 32, raw);
+        for (int c = c0; c < c0 + CH_PER; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + (uint32_t(w * 32) << 16) + acc * BN + c * 32, raw);
+          float4 rcur[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+          if (c + 1 < c0 + CH_PER) load_res(c + 1, rnext);
+          tmem_ld_wait();
+          if (row_ok) epilogue_chunk(e, s.N, row, nbase + c * 32, raw, rcur);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -330,7 +353,7 @@ static void launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmS
   int grid = m_tiles * n_tiles;
   if (grid > num_sms) grid = num_sms;
   if (grid < 1) return;
-  gemm_kernel<BN, CONV><<<grid, 256, C::SMEM, st>>>(tmA, tmB, s, e);
+  gemm_kernel<BN, CONV><<<grid, 384, C::SMEM, st>>>(tmA, tmB, s, e);
 }
 
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
