@@ -211,8 +211,11 @@ def run_ours(args):
     B, nfe = WORK["B"], WORK["nfe"]
     t_ref, t_tgt, T, audio_s = workload_dims(arch)
     W = artifact.make_random_weights(arch, 9527)
-    stream = torch.cuda.current_stream().cuda_stream
-    eng = Engine.from_weights(arch, W, device=local, stream=stream)
+    # a dedicated non-default stream: the engine launches on it and torch's events are recorded on it
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    eng = Engine.from_weights(arch, W, device=local, stream=tstream.cuda_stream)
+    assert eng.stream == tstream.cuda_stream
     del W
     audios, ids = make_inputs(arch, B, T, rank)
     batch = eng.batch([T] * B)
@@ -263,7 +266,9 @@ def run_ours(args):
         e2e_evs.append((e0, e1))
     barrier()
     e2e_ms = float(sum(a.elapsed_time(b) for a, b in e2e_evs))
-    same = all(np.array_equal(o_np[0], pcm0) for _ in range(1))     # e2e result == resident result (same seeds)
+    d = o_np[0].astype(np.float64) - pcm0.astype(np.float64)
+    snr_vs_resident = float(10 * np.log10(np.sum(pcm0.astype(np.float64) ** 2) / (np.sum(d * d) + 1e-30)))
+    same = bool(snr_vs_resident > 40.0)     # e2e result == resident result (same seeds; fp atomics in GRN differ)
 
     # ---- max over ranks
     if dist is not None:

@@ -10,6 +10,10 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#ifndef VV_ATTN_PINGPONG
+#define VV_ATTN_PINGPONG 0
+#endif
+
 namespace vv {
 
 namespace attn {
@@ -37,10 +41,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* k_empty = k_full + KV_STAGES;
   uint64_t* v_full = k_empty + KV_STAGES;
   uint64_t* v_empty = v_full + KV_STAGES;
-  uint64_t* s_full = v_empty + KV_STAGES;  // 2
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = v_empty + KV_STAGES;  // 2: S_t(j) accumulator complete            (MMA -> softmax)
+  uint64_t* s_free = s_full + 2;           // 2: S_t(j) copied to registers              (softmax -> MMA)
+  uint64_t* p_full = s_free + 2;           // 2: P_t(j) in smem, O_t rescaled             (softmax -> MMA)
+  uint64_t* pv_done = p_full + 2;          // 2: O_t += P_t(j) V(j) complete              (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,14 +62,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);   // one commit per q-tile MMA warp
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
       mbar_init(&p_full[i], 128);
-      mbar_init(&o_done[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -98,69 +104,56 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 9 || warp == 11) {
+    // ------------------------------------------------------------------ MMA issuers: one warp per q tile, so the
+    // two tiles form independent S -> softmax -> PV pipelines that only share the K/V ring and the tensor pipe.
+    // S_t(n+1) is issued as soon as softmax has copied S_t(n) to registers, i.e. it runs under softmax_t(n).
     if (lane == 0) {
+      const int t = warp == 9 ? 0 : 1;
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 1);
-      const uint32_t q_addr = smem_u32(smem + Q_OFF);
+      const uint32_t q_addr = smem_u32(smem + Q_OFF) + t * TILE_BYTES;
       const uint32_t k_addr = smem_u32(smem + K_OFF);
       const uint32_t v_addr = smem_u32(smem + V_OFF);
-      const uint32_t p_addr = smem_u32(smem + P_OFF);
-      auto issue_s = [&](int t, int stage) {
-        const uint64_t a0 = make_sdesc_sw128(q_addr + t * TILE_BYTES);
+      const uint32_t p_addr = smem_u32(smem + P_OFF) + 2 * t * TILE_BYTES;
+      const uint32_t d_s = tmem_base + TM_S + t * 128;
+      const uint32_t d_o = tmem_base + TM_O + t * 64;
+      auto issue_s = [&](int stage) {
+        const uint64_t a0 = make_sdesc_sw128(q_addr);
         const uint64_t b0 = make_sdesc_sw128(k_addr + stage * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + TM_S + t * 128, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_ss(d_s, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
       };
-      auto issue_pv = [&](int t, int stage, bool first) {
+      auto issue_pv = [&](int stage, bool first) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t a = make_sdesc_sw128(p_addr + (2 * t + (k >> 2)) * TILE_BYTES) + 2 * (k & 3);
+          const uint64_t a = make_sdesc_sw128(p_addr + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
           const uint64_t b = make_sdesc_sw128(v_addr + stage * TILE_BYTES + k * 2048);
-          umma_ss(tmem_base + TM_O + t * 64, a, b, idesc_o, !(first && k == 0));
+          umma_ss(d_o, a, b, idesc_o, !(first && k == 0));
         }
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      umma_commit(&s_full[0]);
-      issue_s(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&k_empty[0]);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
-        const bool last = (j + 1 == n_kv);
-        mbar_wait(&v_full[stage], phase);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, stage, j == 0);
-        if (!last) {
-          mbar_wait(&k_full[nstage], nphase);
+      int stage = 0, pstage = 0;
+      uint32_t phase = 0, pphase = 0;
+      for (int n = 0; n <= n_kv; ++n) {
+        if (n < n_kv) {
+          if (n > 0) mbar_wait(&s_free[t], (n - 1) & 1);
+          mbar_wait(&k_full[stage], phase);
           tc_fence_after();
-          issue_s(0, nstage);
-          umma_commit(&s_full[0]);
-        } else {
-          umma_commit(&o_done[0]);
+          issue_s(stage);
+          umma_commit(&s_full[t]);
+          umma_commit(&k_empty[stage]);
+          if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
         }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, stage, j == 0);
-        umma_commit(&v_empty[stage]);
-        if (!last) {
-          issue_s(1, nstage);
-          umma_commit(&s_full[1]);
-          umma_commit(&k_empty[nstage]);
-        } else {
-          umma_commit(&o_done[1]);
+        if (n > 0) {
+          mbar_wait(&p_full[t], (n - 1) & 1);
+          mbar_wait(&v_full[pstage], pphase);
+          tc_fence_after();
+          issue_pv(pstage, n == 1);
+          umma_commit(&pv_done[t]);
+          umma_commit(&v_empty[pstage]);
+          if (++pstage == KV_STAGES) { pstage = 0; pphase ^= 1; }
         }
-        stage = nstage;
-        phase = nphase;
       }
     }
   }
@@ -172,9 +165,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_base + lane_base + TM_S + t * 128;
     const uint32_t to = tmem_base + lane_base + TM_O + t * 64;
-    uint8_t* prow = smem + P_OFF + (2 * t) * TILE_BYTES + r * 128;
+    const uint32_t prow = smem_u32(smem + P_OFF) + (2 * t) * TILE_BYTES + r * 128;   // shared-space address
     const int sw = r & 7;
     float m_ref = 0.0f, l = 0.0f;
+#if VV_ATTN_PINGPONG
+    if (t == 1) named_bar_arrive(2, 256);   // warpgroup 0 takes the first MUFU turn
+#endif
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -182,6 +178,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);               // S_t may be overwritten by S_t(j+1) from here on
       const int kv_valid = kv_len - j * 128;
       if (kv_valid < 128) {
 #pragma unroll
@@ -202,14 +200,45 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mxb = fmax3(mxb, __uint_as_float(s[126]), __uint_as_float(s[127]));
       float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
       mx *= p.scale_log2;
+      // lazy rescale decision (the O update itself is deferred until PV(j-1) has retired, below)
+      bool rescale = false;
+      float f = 1.0f;
       if (j == 0) {
         m_ref = mx;
-      } else {
-        const bool need = (mx - m_ref) > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = fmaxf(m_ref, mx);
-          const float f = fast_exp2(m_ref - m_new);
-          m_ref = m_new;
+      } else if (__any_sync(0xffffffffu, (mx - m_ref) > 8.0f)) {
+        const float m_new = fmaxf(m_ref, mx);
+        f = fast_exp2(m_ref - m_new);
+        m_ref = m_new;
+        rescale = true;
+      }
+      // The two softmax warpgroups take turns on the MUFU pipe (ping-pong): while one runs its 128x128 exp2
+      // burst, the other does its TMEM load / max / P store / barrier traffic.
+#if VV_ATTN_PINGPONG
+      named_bar_sync(2 + t, 256);
+#endif
+      uint32_t pk[64];
+      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 columns (16 bytes of bf16)
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
+        sum0 += e[0] + e[4];
+        sum1 += e[1] + e[5];
+        sum2 += e[2] + e[6];
+        sum3 += e[3] + e[7];
+        pk[4 * c] = pack_bf16(e[0], e[1]);
+        pk[4 * c + 1] = pack_bf16(e[2], e[3]);
+        pk[4 * c + 2] = pack_bf16(e[4], e[5]);
+        pk[4 * c + 3] = pack_bf16(e[6], e[7]);
+      }
+#if VV_ATTN_PINGPONG
+      named_bar_arrive(2 + (1 - t), 256);
+#endif
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);   // P_t buffer free again, O_t quiescent
+        tc_fence_after();
+        if (rescale) {
           l *= f;
           uint32_t o[32];
 #pragma unroll
@@ -223,23 +252,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           tmem_st_wait();
         }
       }
-      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 columns (16 bytes of bf16)
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
-        sum0 += e[0] + e[4];
-        sum1 += e[1] + e[5];
-        sum2 += e[2] + e[6];
-        sum3 += e[3] + e[7];
-        uint4 u;
-        u.x = pack_bf16(e[0], e[1]);
-        u.y = pack_bf16(e[2], e[3]);
-        u.z = pack_bf16(e[4], e[5]);
-        u.w = pack_bf16(e[6], e[7]);
+      for (int c = 0; c < 16; ++c) {
         const int atom = c >> 3, chunk = c & 7;
-        *reinterpret_cast<uint4*>(prow + atom * TILE_BYTES + ((chunk ^ sw) << 4)) = u;
+        st_shared_v4(prow + atom * TILE_BYTES + ((chunk ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
+                     pk[4 * c + 3]);
       }
       l += (sum0 + sum1) + (sum2 + sum3);
       fence_proxy_async_smem();
@@ -247,7 +264,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mbar_arrive(&p_full[t]);
     }
     // ---- finalize: O / l -> bf16
-    mbar_wait(&o_done[t], 0);
+    mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     const int qrow = q0 + t * 128 + r;
     const float inv = 1.0f / l;

@@ -23,6 +23,9 @@ def _ptr(a: Optional[np.ndarray]):
 class Engine:
     def __init__(self, arch: ArchConfig, device: int = 0, stream: Optional[int] = None):
         arch.validate()
+        if stream == 0:
+            raise ValueError("stream=0 is the legacy default stream (no CUDA-graph capture, implicit syncs): pass a "
+                             "non-default cudaStream_t handle, or None for an engine-owned stream")
         self.lib = _lib.load()
         self.arch = arch
         self.device = device
