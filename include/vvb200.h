@@ -98,6 +98,8 @@ int64_t vv_get_tensor(vv_batch* b, int idx, const char* name, float* out, int64_
 int vv_set_noise(vv_batch* b, int idx, const float* noise);
 /* override the conditioning (the `cat_mel_text*` feeds of a single transformer session call) */
 int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, const float* cat_mel_text_drop);
+/* override ref_signal_len (the second feed of a standalone `decode` session call, tts_engine.py:182-185) */
+int vv_set_ref_len(vv_batch* b, int idx, int64_t ref_len);
 int vv_sync(vv_engine* e);
 /* parity aid: input embedding + the first n_layers DiT blocks of `step` (no Euler update), for vv_get_tensor taps
  * ("x0", "hidden", "qkv", "attn", "hb", "h1b", "ffb", "cond_proj", "v") */

@@ -109,6 +109,49 @@ def main():
     out["xf_plain"] = AP.concatenate_with_crossfade(waves, 0.1, 24000)
     out["xf_plain_short"] = AP.concatenate_with_crossfade([waves[4], waves[2]], 0.1, 24000)
     np.savez_compressed(os.path.join(HERE, "host_audio.npz"), **out)
+
+    # ------------------------------------------------------------------ TTSEngine._prepare_inputs (core/tts_engine.py:43-131)
+    # the package imports onnxruntime at import time; our onnxruntime-shaped shim satisfies that import only
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from vietvoice_tts_b200 import ort_shim
+    ort_shim.install()
+    sys.path.insert(0, "/root/reference")
+    from vietvoicetts.core.tts_engine import TTSEngine as RefEngine
+    from vietvoicetts.core.model_config import ModelConfig as RefConfig
+
+    class FakeAudio:
+        def __init__(self, n):
+            self.n = n
+
+        def load_audio(self, path, sr):
+            return (np.arange(self.n) % 1000).astype(np.int16)
+
+    long_text = " ".join(raw_texts[8:9] * 6)
+    prep = []
+    for n_samples, ref_text, target, speed, max_dur in [
+        (144000, "xin chào, đây là giọng mẫu.", "Xin chào Việt Nam.", 0.9, 20.0),
+        (144000, "xin chào, đây là giọng mẫu.", long_text, 0.9, 20.0),
+        (217689, "một câu tham chiếu khá dài để làm mẫu giọng nói, có dấu phẩy.", long_text, 1.0, 20.0),
+        (72000, "ngắn.", "a", 0.5, 20.0),
+        (100000, "câu mẫu thứ ba!", long_text + " " + long_text, 1.3, 15.0),
+        (144000, "xin chào.", "supercalifragilisticexpialidocious " * 30, 0.9, 20.0),
+    ]:
+        cfg = RefConfig.__new__(RefConfig)
+        for k, v in dict(sample_rate=24000, hop_length=256, speed=speed, pause_punctuation=r".,?!:",
+                         max_chunk_duration=max_dur, min_target_duration=1.0).items():
+            setattr(cfg, k, v)
+        eng = RefEngine.__new__(RefEngine)
+        eng.config = cfg
+        eng.text_processor = tp
+        eng.audio_processor = FakeAudio(n_samples)
+        res = eng._prepare_inputs("unused.wav", ref_text, target)
+        prep.append({"n_samples": n_samples, "ref_text": ref_text, "target": target, "speed": speed,
+                     "max_chunk_duration": max_dur,
+                     "chunks": [{"ids": r[1].tolist(), "max_duration": int(r[2][0]), "time_step": int(r[3][0])}
+                                for r in res]})
+    with open(os.path.join(HERE, "host_prepare_inputs.json"), "w", encoding="utf-8") as f:
+        json.dump(prep, f, ensure_ascii=False)
+    print("wrote host_prepare_inputs.json:", [len(p["chunks"]) for p in prep])
     print("wrote host_text.json (%d cases), host_audio.npz (%d arrays)" % (len(cases), len(out)))
 
 

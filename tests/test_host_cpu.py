@@ -120,3 +120,50 @@ def test_wav_roundtrip_and_load(tmp_path):
         AudioProcessor.save_audio(np.array([], dtype=np.int16), p, sr)
     with pytest.raises(RuntimeError):
         AudioProcessor.load_audio(b"\x00\x00\x00\x20ftypM4A not a wav", sr)
+
+
+def test_prepare_inputs_matches_reference(tp):
+    """TTSEngine._prepare_inputs: duration model, chunking and ids vs the reference's own method
+    (/root/reference/vietvoicetts/core/tts_engine.py:43-131), goldens from make_host_goldens.py."""
+    from vietvoice_tts_b200.host.tts_engine import TTSEngine
+    from vietvoice_tts_b200.host.model_config import ModelConfig
+
+    class FakeAudio:
+        def __init__(self, n):
+            self.n = n
+
+        def load_audio(self, path, sr):
+            return (np.arange(self.n) % 1000).astype(np.int16)
+
+    with open(os.path.join(G, "host_prepare_inputs.json"), encoding="utf-8") as f:
+        cases = json.load(f)
+    assert sum(len(c["chunks"]) for c in cases) > 100
+    for c in cases:
+        cfg = ModelConfig.__new__(ModelConfig)
+        for k, v in dict(sample_rate=24000, hop_length=256, speed=c["speed"], pause_punctuation=r".,?!:",
+                         max_chunk_duration=c["max_chunk_duration"], min_target_duration=1.0).items():
+            setattr(cfg, k, v)
+        eng = TTSEngine.__new__(TTSEngine)
+        eng.config, eng.text_processor, eng.audio_processor, eng.sample_cache = cfg, tp, FakeAudio(c["n_samples"]), {}
+        got = eng._prepare_inputs("unused.wav", c["ref_text"], c["target"])
+        assert len(got) == len(c["chunks"])
+        for (audio, ids, max_dur, ts), ref in zip(got, c["chunks"]):
+            assert audio.shape == (1, 1, c["n_samples"]) and audio.dtype == np.int16
+            assert ids.dtype == np.int32 and ids.tolist() == ref["ids"]
+            assert max_dur.dtype == np.int64 and int(max_dur[0]) == ref["max_duration"]
+            assert ts.dtype == np.int32 and int(ts[0]) == ref["time_step"] == 0
+
+
+def test_model_config_contract(tmp_path):
+    from vietvoice_tts_b200.host.model_config import ModelConfig, TTSConfig
+    (tmp_path / "model-bin.pt").write_bytes(b"x")
+    c = ModelConfig(model_cache_dir=str(tmp_path))
+    assert (c.nfe_step, c.fuse_nfe, c.sample_rate, c.hop_length, c.random_seed, c.speed) == (32, 1, 24000, 256, 9527, 0.9)
+    assert c.max_chunk_duration == 20.0 and c.pause_punctuation == r".,?!:" and TTSConfig is ModelConfig
+    assert ModelConfig.from_dict(c.to_dict()).to_dict() == c.to_dict()
+    # /root/reference/tests/test_edge_cases.py:330-357
+    for bad in (dict(speed=0.05), dict(speed=5.5), dict(nfe_step=0), dict(nfe_step=101)):
+        with pytest.raises(ValueError):
+            ModelConfig(model_cache_dir=str(tmp_path), **bad)
+    with pytest.raises(RuntimeError):          # no network, no cached file -> "Model validation failed"
+        ModelConfig(model_cache_dir=str(tmp_path / "empty"), model_url="http://127.0.0.1:9/none")

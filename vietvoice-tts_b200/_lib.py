@@ -84,6 +84,7 @@ def load() -> C.CDLL:
             "vv_get_tensor": (I64, [P, I, C.c_char_p, P, I64]),
             "vv_set_noise": (I, [P, I, P]),
             "vv_set_cond": (I, [P, I, P, P]),
+            "vv_set_ref_len": (I, [P, I, I64]),
             "vv_sync": (I, [P]),
             "vv_debug_partial_step": (I, [P, I, I, I]),
             "vv_synthesize_batch": (I, [P, C.POINTER(VVRequest), I, I, U64]),

@@ -1252,6 +1252,13 @@ extern "C" int vv_set_noise(vv_batch* b, int idx, const float* noise) {
   return 0;
 }
 
+extern "C" int vv_set_ref_len(vv_batch* b, int idx, int64_t ref_len) {
+  if (!b || idx < 0 || idx >= b->B || ref_len < 0 || ref_len > b->T[idx]) return fail(VV_ERR_ARG, "vv_set_ref_len: bad argument");
+  b->ref_len[idx] = (int)ref_len;
+  b->decoded = false;
+  return 0;
+}
+
 extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, const float* cat_mel_text_drop) {
   if (!b || !cat_mel_text || !cat_mel_text_drop || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_set_cond: bad argument");
   vv_engine* e = b->e;

@@ -207,6 +207,10 @@ class Batch:
         nz = np.ascontiguousarray(noise, dtype=np.float32).reshape(self.T[idx], self.e.arch.n_mel)
         _lib.check(self.lib.vv_set_noise(self._h, idx, _ptr(nz)))
 
+    def set_ref_len(self, idx: int, ref_len: int) -> None:
+        _lib.check(self.lib.vv_set_ref_len(self._h, idx, int(ref_len)))
+        self.ref_len[idx] = int(ref_len)
+
     def set_cond(self, idx: int, cat_c: np.ndarray, cat_u: np.ndarray) -> None:
         a = self.e.arch
         c = np.ascontiguousarray(cat_c, dtype=np.float32).reshape(self.T[idx], a.cond_dim)
