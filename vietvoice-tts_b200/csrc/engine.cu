@@ -623,7 +623,7 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   AB(b->tx, (size_t)M * a.text_dim);
   AB(b->t_tmp, (size_t)M * a.text_dim);
   AB(b->t_ff, (size_t)M * a.text_ff);
-  AB(b->gx2, (size_t)2 * B * a.text_ff);
+  AB(b->gx2, (size_t)2 * B * ((b->maxT + 63) / 64) * a.text_ff);
   AB(b->nx, (size_t)2 * B * a.text_ff);
   AB(b->t_hb, (size_t)M * a.text_dim);
   AB(b->t_ffb, (size_t)M * a.text_ff);

@@ -137,10 +137,11 @@ void launch_dwconv_rows(const float* x, const int32_t* row_pos, const int32_t* r
   if (n) dwconv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, row_pos, row_len, w, b, rows, C, K, out);
 }
 
-// GRN (ConvNeXt-V2): per sequence, per channel L2 norm over TIME.
+// GRN (ConvNeXt-V2): per sequence, per channel L2 norm over TIME.  Two-stage reduction with a fixed summation
+// order (no float atomics): the same inputs give bit-identical outputs on every run.
 __global__ void grn_sumsq_kernel(const float* __restrict__ h, const int32_t* __restrict__ seq_off,
                                  const int32_t* __restrict__ seq_len, int C, int rows_per_block,
-                                 float* __restrict__ gx2) {
+                                 float* __restrict__ partial /* [n_seq][gridDim.y][C] */) {
   const int seq = blockIdx.z;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -153,14 +154,20 @@ __global__ void grn_sumsq_kernel(const float* __restrict__ h, const int32_t* __r
     const float v = h[(size_t)(off + r) * C + c];
     s += v * v;
   }
-  if (r1 > r0) atomicAdd(gx2 + (size_t)seq * C + c, s);
+  partial[((size_t)seq * gridDim.y + blockIdx.y) * C + c] = s;
 }
-__global__ void grn_norm_kernel(const float* __restrict__ gx2, int C, float* __restrict__ nx) {
+__global__ void grn_norm_kernel(const float* __restrict__ partial, int n_blk, int C, float* __restrict__ nx) {
   // one block per sequence
   __shared__ float red[32];
   const int seq = blockIdx.x;
   float s = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s += sqrtf(gx2[(size_t)seq * C + c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g2 = 0.f;
+    for (int k = 0; k < n_blk; ++k) g2 += partial[((size_t)seq * n_blk + k) * C + c];
+    const float g = sqrtf(g2);
+    nx[(size_t)seq * C + c] = g;      // Gx for now; normalised below
+    s += g;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -173,8 +180,7 @@ __global__ void grn_norm_kernel(const float* __restrict__ gx2, int C, float* __r
   }
   __syncthreads();
   const float mean = red[0];
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    nx[(size_t)seq * C + c] = sqrtf(gx2[(size_t)seq * C + c]) / (mean + 1e-6f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) nx[(size_t)seq * C + c] = nx[(size_t)seq * C + c] / (mean + 1e-6f);
 }
 __global__ void grn_apply_kernel(const float* __restrict__ h, const int32_t* __restrict__ row_seq,
                                  const float* __restrict__ nx, const float* __restrict__ g,
@@ -194,11 +200,10 @@ void launch_grn(const float* h, const int32_t* seq_off, const int32_t* seq_len, 
                 int max_len, int rows, int C, const float* g, const float* b, float* gx2, float* nx, bf16* out,
                 cudaStream_t st) {
   if (rows == 0 || n_seq == 0) return;
-  cudaMemsetAsync(gx2, 0, (size_t)n_seq * C * sizeof(float), st);
-  const int rpb = 64;
+  const int rpb = 64;   // gx2 holds [n_seq][ceil(max_len/64)][C] partial sums
   dim3 grid((C + 127) / 128, (max_len + rpb - 1) / rpb, n_seq);
   grn_sumsq_kernel<<<grid, 128, 0, st>>>(h, seq_off, seq_len, C, rpb, gx2);
-  grn_norm_kernel<<<n_seq, 256, 0, st>>>(gx2, C, nx);
+  grn_norm_kernel<<<n_seq, 256, 0, st>>>(gx2, grid.y, C, nx);
   const size_t n = (size_t)rows * C;
   grn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, row_seq, nx, g, b, rows, C, out);
 }
