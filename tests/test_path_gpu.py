@@ -131,6 +131,6 @@ def test_full_arch_single_step_vs_oracle(need_gpu):
     solo = eng.synthesize_batch(audios[1:2], idl[1:2], [T], nfe=8, seed=11, chunk_keys=[1])
     assert a1[0].shape[0] == (T - 563 - 1) * 256 and a1[2].shape[0] == (1200 - 563 - 1) * 256
     for x, y in zip(a1, a2):
-        assert snr_db(x, y) > 60.0                       # replay of the same batch
+        assert np.array_equal(x, y)                      # replay of the same batch is bit-identical
     assert snr_db(solo[0], a1[1]) > 25.0                 # chunk 1 alone == chunk 1 inside a ragged batch
     eng.close()

@@ -13,6 +13,7 @@ path is `host.tts_engine.TTSEngine`, which hands whole chunks to `Engine.synthes
 """
 from __future__ import annotations
 
+import os
 import sys
 import threading
 from typing import Dict, List, Optional, Sequence
@@ -157,7 +158,7 @@ class InferenceSession:
         arch = ArchConfig(**{f: getattr(carch, f) for f, _ in VVArch._fields_})
         self._options = sess_options or SessionOptions()
         self._providers = list(providers) if providers else get_available_providers()
-        device = 0
+        device = int(os.environ.get("VVB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))   # one process per GPU
         for p in self._providers:
             if isinstance(p, tuple) and isinstance(p[1], dict) and "device_id" in p[1]:
                 device = int(p[1]["device_id"])
