@@ -24,7 +24,8 @@ struct GemmCfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulators
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int PAR_BYTES = 8 * 2 * 32 * 16;  // per epilogue warp: 32 float4 of bias + 32 float4 of gate
+  static constexpr int SMEM = STAGES * STAGE_BYTES + BAR_BYTES + PAR_BYTES + 1024;
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -40,8 +41,11 @@ __device__ __forceinline__ float mish_f(float x) {
   return x * __fdividef(n, n + 2.0f);
 }
 
+// sb / sg: this chunk's 32 bias / gate values staged in shared memory by the warp at tile start (a global __ldg
+// right before use cost one exposed L2 latency per chunk for each of them: the L1 is thrashed by the residual stream)
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row, int n0, const uint32_t (&raw)[32],
-                                               const float4 (&rpre)[8]) {
+                                               const float4 (&rpre)[8], const float4* sb, const float4* sg,
+                                               bool wide) {
   int nvalid = N - n0;
   if (nvalid <= 0) return;
   const bool full = nvalid >= 32;
@@ -52,10 +56,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
 
   if (e.bias) {
     if (full) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
+        const float4 b = sb[j];
         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     } else {
@@ -91,10 +94,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
   }
   if (e.gate) {
     if (full) {
-      const float4* g4 = reinterpret_cast<const float4*>(e.gate + n0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 g = __ldg(g4 + j);
+        const float4 g = sg[j];
         v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
       }
     } else {
@@ -123,7 +125,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
   }
   if (e.out_f32) {
     float* o = e.out_f32 + (size_t)row * e.ld_f32 + n0;
-    if (full) {
+    if (full && wide) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        stg256(o + 8 * j, make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+               make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+    } else if (full) {
       float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -135,7 +142,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
   }
   if (e.out_bf16) {
     bf16* o = e.out_bf16 + (size_t)row * e.ld_bf16 + n0;
-    if (full) {
+    if (full && wide) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 u0, u1;
+        u0.x = pack_bf16(v[16 * j], v[16 * j + 1]);       u0.y = pack_bf16(v[16 * j + 2], v[16 * j + 3]);
+        u0.z = pack_bf16(v[16 * j + 4], v[16 * j + 5]);   u0.w = pack_bf16(v[16 * j + 6], v[16 * j + 7]);
+        u1.x = pack_bf16(v[16 * j + 8], v[16 * j + 9]);   u1.y = pack_bf16(v[16 * j + 10], v[16 * j + 11]);
+        u1.z = pack_bf16(v[16 * j + 12], v[16 * j + 13]); u1.w = pack_bf16(v[16 * j + 14], v[16 * j + 15]);
+        stg256_u(o + 16 * j, u0, u1);
+      }
+    } else if (full) {
       uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -250,6 +267,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // 8 epilogue warps: warp%4 selects the TMEM lane quadrant (rows), (warp-4)/4 selects the column half
     const int w = warp & 3;
     const int half = (warp - 4) >> 2;
+    const bool wide = ((reinterpret_cast<uintptr_t>(e.resid) | reinterpret_cast<uintptr_t>(e.out_f32) |
+                        reinterpret_cast<uintptr_t>(e.out_bf16)) & 31) == 0 &&
+                      (e.ld_resid % 8) == 0 && (e.ld_f32 % 8) == 0 && (e.ld_bf16 % 16) == 0;
     constexpr int CH = BN / 32;                      // 32-column chunks per tile
     constexpr int CH_PER = CH >= 2 ? CH / 2 : 1;     // chunks per epilogue warp
     int it = 0;
@@ -267,12 +287,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       auto load_res = [&](int c, float4 (&r)[8]) {
         const int n0 = nbase + c * 32;
         if (has_res && n0 + 32 <= s.N) {
-          const float4* r4 = reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_resid + n0);
+          const float* rp = e.resid + (size_t)row * e.ld_resid + n0;
+          if (wide) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = r4[j];
+            for (int j = 0; j < 4; ++j) ldg256_stream(rp + 8 * j, r[2 * j], r[2 * j + 1]);
+          } else {
+            const float4* r4 = reinterpret_cast<const float4*>(rp);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = r4[j];
+          }
         }
       };
       if (CH >= 2 || half == 0) load_res(c0, rnext);
+      // stage this warp's bias / gate columns (CH_PER*32 floats each) in shared memory
+      float4* sbias = reinterpret_cast<float4*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + (warp - 4) * 64;
+      float4* sgate = sbias + 32;
+      {
+        const int ncol = nbase + c0 * 32 + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (lane < CH_PER * 8 && ncol + 4 <= s.N) {
+          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + ncol));
+          if (e.gate) g4 = __ldg(reinterpret_cast<const float4*>(e.gate + ncol));
+        }
+        __syncwarp();
+        sbias[lane] = b4;
+        sgate[lane] = g4;
+        __syncwarp();
+      }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       if (CH >= 2 || half == 0) {
@@ -285,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
           if (c + 1 < c0 + CH_PER) load_res(c + 1, rnext);
           tmem_ld_wait();
-          if (row_ok) epilogue_chunk(e, s.N, row, nbase + c * 32, raw, rcur);
+          if (row_ok) epilogue_chunk(e, s.N, row, nbase + c * 32, raw, rcur, sbias + (c - c0) * 8, sgate + (c - c0) * 8, wide);
         }
       }
       tc_fence_before();
