@@ -68,3 +68,9 @@ if what in ("gemm", "all"):
             timeit(fn, 2.0 * M * N * K, f"gemm {name} N={N} K={K} bn={bn}")
 torch.cuda.synchronize()
 lib.vv_engine_destroy(h)
+if hasattr(lib, "vv_attn_timing_dump") or os.environ.get("VVB200_LIB", "").find("_T") >= 0:
+    try:
+        import ctypes
+        ctypes.CDLL(os.environ["VVB200_LIB"]).vv_attn_timing_dump()
+    except Exception as exc:
+        print("no timing dump:", exc)

@@ -10,11 +10,26 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <stdio.h>
+
 #ifndef VV_ATTN_PINGPONG
 #define VV_ATTN_PINGPONG 0
 #endif
 
+#ifndef VV_ATTN_TIMING
+#define VV_ATTN_TIMING 0
+#endif
+#if VV_ATTN_TIMING
+#define TICK(i) do { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
+
 namespace vv {
+
+#if VV_ATTN_TIMING
+__device__ long long g_attn_timing[8];
+#endif
 
 namespace attn {
 constexpr int KV_STAGES = 3;
@@ -168,11 +183,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t prow = smem_u32(smem + P_OFF) + (2 * t) * TILE_BYTES + r * 128;   // shared-space address
     const int sw = r & 7;
     float m_ref = 0.0f, l = 0.0f;
+#if VV_ATTN_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
 #if VV_ATTN_PINGPONG
     if (t == 1) named_bar_arrive(2, 256);   // warpgroup 0 takes the first MUFU turn
 #endif
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
+      TICK(0);   // wait S
       tc_fence_after();
       uint32_t s[128];
 #pragma unroll
@@ -180,6 +200,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);               // S_t may be overwritten by S_t(j+1) from here on
+      TICK(1);   // tmem ld
       const int kv_valid = kv_len - j * 128;
       if (kv_valid < 128) {
 #pragma unroll
@@ -200,6 +221,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mxb = fmax3(mxb, __uint_as_float(s[126]), __uint_as_float(s[127]));
       float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
       mx *= p.scale_log2;
+      TICK(2);   // mask + max
       // lazy rescale decision (the O update itself is deferred until PV(j-1) has retired, below)
       bool rescale = false;
       float f = 1.0f;
@@ -235,8 +257,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #if VV_ATTN_PINGPONG
       named_bar_arrive(2 + (1 - t), 256);
 #endif
+      TICK(3);   // exp + pack (incl. ping-pong wait)
       if (j > 0) {
         mbar_wait(&pv_done[t], (j - 1) & 1);   // P_t buffer free again, O_t quiescent
+        TICK(4);   // wait PV
         tc_fence_after();
         if (rescale) {
           l *= f;
@@ -262,9 +286,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      TICK(5);   // rescale + P store + fence + arrive
     }
     // ---- finalize: O / l -> bf16
     mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+    TICK(6);   // final wait
     tc_fence_after();
     const int qrow = q0 + t * 128 + r;
     const float inv = 1.0f / l;
@@ -290,11 +316,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         }
       }
     }
+#if VV_ATTN_TIMING
+    TICK(7);   // O store
+    if (lane == 0 && blockIdx.x % 97 == 0)
+      for (int i = 0; i < 8; ++i)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_attn_timing[i]), (unsigned long long)tacc[i]);
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 10) tmem_dealloc(tmem_base, 512);
 }
+
+#if VV_ATTN_TIMING
+extern "C" void vv_attn_timing_dump() {
+  long long h[8];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_attn_timing, sizeof(h));
+  const char* names[8] = {"wait_S", "tmem_ld", "mask_max", "exp_pack", "wait_PV", "store_arrive", "final_wait", "O_store"};
+  long long tot = 0;
+  for (int i = 0; i < 8; ++i) tot += h[i];
+  for (int i = 0; i < 8; ++i) printf("%-14s %12lld  %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+  long long z[8] = {0};
+  cudaMemcpyToSymbol(g_attn_timing, z, sizeof(z));
+}
+#endif
 
 void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
   static bool attr_set = false;
