@@ -2,8 +2,8 @@
 // One CTA = one head x 256 query rows (two 128-row tiles, each owned by one softmax warpgroup).
 //   S_t = Q_t K^T      : tcgen05.mma M128 N128 K64, accumulator in TMEM (128 cols per tile)
 //   softmax (online, lazy rescale) in registers: one thread per query row, no shuffles
-//   P_t -> bf16 in 128B-swizzled smem, O_t += P_t V : tcgen05.mma M128 N64 K128, V consumed MN-major straight
-//   from the TMA tile (no transpose), O accumulator in TMEM (64 cols per tile)
+//   P_t -> bf16 written back to TMEM (tcgen05.st, 64 cols per tile); O_t += P_t V : tcgen05.mma M128 N64 K128 with the
+//   A operand read from TMEM and V consumed MN-major straight from the TMA tile (no transpose); O in TMEM (64 cols)
 // RoPE has already been applied to q/k by the QKV GEMM epilogue.
 //
 // Replaces the attention sub-graph of `transformer.onnx` (/root/reference/vietvoicetts/core/tts_engine.py:161-172).
@@ -16,6 +16,18 @@
 #define VV_ATTN_PINGPONG 0
 #endif
 
+#ifndef VV_ATTN_POLY_N
+#define VV_ATTN_POLY_N 0     // of every VV_ATTN_POLY_MOD softmax elements, this many take the FMA-pipe exp2
+#endif
+#ifndef VV_ATTN_POLY_MOD
+#define VV_ATTN_POLY_MOD 4
+#endif
+#ifndef VV_ATTN_P_TMEM
+#define VV_ATTN_P_TMEM 1    // 1: P goes back to TMEM (tcgen05.st) and the PV MMA reads its A operand from TMEM
+#endif
+#ifndef VV_ATTN_SKEW_NS
+#define VV_ATTN_SKEW_NS 0
+#endif
 #ifndef VV_ATTN_TIMING
 #define VV_ATTN_TIMING 0
 #endif
@@ -43,6 +55,7 @@ constexpr int SMEM = BAR_OFF + 256 + 1024;
 constexpr int THREADS = 384;
 constexpr uint32_t TM_S = 0;     // S0 @0, S1 @128
 constexpr uint32_t TM_O = 256;   // O0 @256, O1 @320
+constexpr uint32_t TM_P = 384;   // P0 @384, P1 @448 (bf16 pairs: 64 columns per tile) — only with VV_ATTN_P_TMEM
 }  // namespace attn
 
 __global__ void __launch_bounds__(attn::THREADS, 1)
@@ -142,9 +155,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       auto issue_pv = [&](int stage, bool first) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const uint64_t a = make_sdesc_sw128(p_addr + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
           const uint64_t b = make_sdesc_sw128(v_addr + stage * TILE_BYTES + k * 2048);
+#if VV_ATTN_P_TMEM
+          umma_ts(d_o, tmem_base + TM_P + t * 64 + k * 8, b, idesc_o, !(first && k == 0));
+#else
+          const uint64_t a = make_sdesc_sw128(p_addr + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
           umma_ss(d_o, a, b, idesc_o, !(first && k == 0));
+#endif
         }
       };
       mbar_wait(q_full, 0);
@@ -180,8 +197,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t ts = tmem_base + lane_base + TM_S + t * 128;
     const uint32_t to = tmem_base + lane_base + TM_O + t * 64;
+#if !VV_ATTN_P_TMEM
     const uint32_t prow = smem_u32(smem + P_OFF) + (2 * t) * TILE_BYTES + r * 128;   // shared-space address
     const int sw = r & 7;
+#endif
     float m_ref = 0.0f, l = 0.0f;
 #if VV_ATTN_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -189,6 +208,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #endif
 #if VV_ATTN_PINGPONG
     if (t == 1) named_bar_arrive(2, 256);   // warpgroup 0 takes the first MUFU turn
+#endif
+#if VV_ATTN_SKEW_NS > 0
+    if (t == 1) __nanosleep(VV_ATTN_SKEW_NS);   // start tile 1 half an iteration late: its exp2 burst then falls under tile 0's non-MUFU phases
 #endif
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
@@ -244,7 +266,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 columns (16 bytes of bf16)
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref));
+        for (int i = 0; i < 8; ++i) {
+          const float xs = fmaf(__uint_as_float(s[c * 8 + i]), p.scale_log2, -m_ref);
+          e[i] = (i % VV_ATTN_POLY_MOD) < VV_ATTN_POLY_N ? poly_exp2(xs) : fast_exp2(xs);
+        }
         sum0 += e[0] + e[4];
         sum1 += e[1] + e[5];
         sum2 += e[2] + e[6];
@@ -276,12 +301,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           tmem_st_wait();
         }
       }
+#if VV_ATTN_P_TMEM
+      tmem_st32(tmem_base + lane_base + TM_P + t * 64, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(tmem_base + lane_base + TM_P + t * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+#else
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int atom = c >> 3, chunk = c & 7;
         st_shared_v4(prow + atom * TILE_BYTES + ((chunk ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
                      pk[4 * c + 3]);
       }
+#endif
       l += (sum0 + sum1) + (sum2 + sum3);
       fence_proxy_async_smem();
       tc_fence_before();
