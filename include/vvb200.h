@@ -143,7 +143,8 @@ typedef struct vv_gemm_epilogue {
   int32_t rope_dim, rope_off2;
   int32_t act;              /* 0 none, 1 gelu-tanh, 2 gelu-erf, 3 mish */
 } vv_gemm_epilogue;
-/* C[M,N] = A[M,K] (bf16, ld lda) * B[N,K]^T (bf16, ld ldb), fused epilogue.  K % 64 == 0.  bn in {64,128,256}. */
+/* C[M,N] = A[M,K] (bf16, ld lda) * B[N,K]^T (bf16, ld ldb), fused epilogue.  K % 64 == 0.  bn in {64,128,256} = 1-CTA tile
+   width; bn = 512 = 256x256 tile on a 2-CTA pair (needs N % 256 == 0); any other value lets the engine choose. */
 int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                  const vv_gemm_epilogue* epi, int bn);
 /* grouped conv over rows (implicit GEMM): X bf16 [M, groups*64], Wt bf16 [groups*taps*64, 64] */

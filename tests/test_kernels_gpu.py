@@ -80,6 +80,118 @@ def test_gemm_persistent_many_tiles(eng):
     assert rel_err(out, ref) < 4e-3
 
 
+# ---------------------------------------------------------------------------------------------- CTA-pair kernel
+@pytest.mark.parametrize("M,N,K", [
+    (256, 256, 64), (128, 256, 128), (300, 512, 256), (1000, 1024, 1024), (3034, 3072, 1024), (3034, 1024, 2048),
+    (257, 256, 64 * 7),
+])
+def test_gemm_pair_plain(eng, M, N, K):
+    """bn=512: 256x256 tile on a 2-CTA cluster (tcgen05 cta_group::2); ragged M, rings wrapping, odd pair count"""
+    lib, h = eng
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M + 3, N), float("nan"), device="cuda")
+    run_gemm(lib, h, A, B, M, N, K, 512, bias=bias, out_f32=out, ld_f32=N)
+    ref = A.float() @ B.float().t() + bias
+    assert torch.isfinite(out[:M]).all()
+    assert rel_err(out[:M], ref) < 2e-5
+    assert torch.isnan(out[M:]).all()                 # nothing written past M
+
+
+def test_gemm_pair_many_tiles_bf16_gelu(eng):
+    """more pair tiles than clusters: smem ring and both TMEM accumulators wrap; bf16 + GELU-tanh epilogue (ffn-up)"""
+    lib, h = eng
+    M, N, K = 128 * 41, 256 * 8, 320
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    run_gemm(lib, h, A, B, M, N, K, 512, bias=bias, act=1, out_bf16=out, ld_bf16=N)
+    ref = torch.nn.functional.gelu(A.float() @ B.float().t() + bias, approximate="tanh")
+    assert rel_err(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K,masked", [(700, 256, 512, True), (5000, 1024, 1024, False), (24272, 1024, 256, False)])
+def test_gemm_pair_gate_residual_inplace(eng, M, N, K, masked):
+    """x += gate * (A B^T + bias) in place through the TMA-staged residual epilogue (out-proj / ffn-down form)"""
+    lib, h = eng
+    g = torch.Generator(device="cuda").manual_seed(11 + M)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gate = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M + 2, N, device="cuda", generator=g)
+    x0 = x.clone()
+    kw = {}
+    mask = None
+    if masked:
+        mask = (torch.rand(M, device="cuda", generator=g) > 0.2).to(torch.uint8)
+        kw["row_mask"] = mask
+    run_gemm(lib, h, A, B, M, N, K, 512, bias=bias, gate=gate, resid=x, ld_resid=N, out_f32=x, ld_f32=N, **kw)
+    ref = x0[:M] + gate * (A.float() @ B.float().t() + bias)
+    if masked:
+        ref = ref * mask[:, None].float()
+    assert rel_err(x[:M], ref) < 2e-5
+    assert torch.equal(x[M:], x0[M:])                 # rows past M untouched
+
+
+def test_gemm_pair_residual_separate_out_and_bf16(eng):
+    """residual + fp32 + bf16 outputs (input-embedding form): the direct (non-TMA) pair epilogue"""
+    lib, h = eng
+    M, N, K = 1500, 512, 128
+    g = torch.Generator(device="cuda").manual_seed(21)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    r = torch.randn(M, N, device="cuda", generator=g)
+    o = torch.empty(M, N, device="cuda")
+    ob = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    run_gemm(lib, h, A, B, M, N, K, 512, resid=r, ld_resid=N, out_f32=o, ld_f32=N, out_bf16=ob, ld_bf16=N)
+    ref = A.float() @ B.float().t() + r
+    assert rel_err(o, ref) < 2e-5
+    assert rel_err(ob, ref) < 4e-3
+
+
+def test_gemm_pair_rope_epilogue(eng):
+    lib, h = eng
+    dim, M = 256, 1400
+    N, K = 3 * dim, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    pos = torch.randint(0, 2000, (M,), device="cuda", generator=g, dtype=torch.int32)
+    out = torch.empty(M, N, device="cuda")
+    run_gemm(lib, h, A, B, M, N, K, 512, bias=bias, out_f32=out, ld_f32=N, row_pos=pos, rope_dim=64, rope_off2=dim)
+    pre = A.float() @ B.float().t() + bias
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, device="cuda", dtype=torch.float64) / 64))
+    ang = pos.double()[:, None] * inv[None]
+    cos = torch.repeat_interleave(torch.cos(ang), 2, -1).float()
+    sin = torch.repeat_interleave(torch.sin(ang), 2, -1).float()
+
+    def rot(x):
+        x1, x2 = x[..., 0::2], x[..., 1::2]
+        return torch.stack((-x2, x1), -1).reshape(x.shape)
+
+    ref = pre.clone()
+    for o in (0, dim):
+        seg = pre[:, o:o + 64]
+        ref[:, o:o + 64] = seg * cos + rot(seg) * sin
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_gemm_pair_rejects_bad_n(eng):
+    lib, h = eng
+    A = torch.zeros(256, 64, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(192, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(256, 192, device="cuda")
+    ep = _lib.VVGemmEpilogue()
+    ep.out_f32 = out.data_ptr(); ep.ld_f32 = 192
+    assert lib.vv_gemm_bf16(h, P(A), 64, P(B), 64, 256, 192, 64, C.byref(ep), 512) < 0
+
+
 @pytest.mark.parametrize("act", [1, 2, 3])
 def test_gemm_activation_bf16(eng, act):
     lib, h = eng

@@ -13,6 +13,7 @@ run() {  # name, timeout, pytest args...
 }
 : > gpurun_out/summary.txt
 run gemm_plain 240 tests/test_kernels_gpu.py -m gpu -k "gemm_plain or persistent" || exit 0
+run gemm_pair 240 tests/test_kernels_gpu.py -m gpu -k "gemm_pair" || exit 0
 run gemm_epi 240 tests/test_kernels_gpu.py -m gpu -k "activation or gate_residual or rope"
 run conv 180 tests/test_kernels_gpu.py -m gpu -k "conv_rows"
 run ln 120 tests/test_kernels_gpu.py -m gpu -k "ln_modulate"

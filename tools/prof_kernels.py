@@ -63,9 +63,12 @@ if what in ("gemm", "all"):
         else:
             o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             ep.out_bf16 = o.data_ptr(); ep.ld_bf16 = N; ep.act = act
-        for bn in (128, 256):
+        for bn in (256, 512):
             fn = lambda: _lib.check(lib.vv_gemm_bf16(h, P(A), K, P(B), K, M, N, K, C.byref(ep), bn))
             timeit(fn, 2.0 * M * N * K, f"gemm {name} N={N} K={K} bn={bn}")
+            if bn == 512 and hasattr(lib, "vv_gemm_timing_dump"):
+                sys.stdout.flush()
+                lib.vv_gemm_timing_dump()
 torch.cuda.synchronize()
 lib.vv_engine_destroy(h)
 if hasattr(lib, "vv_attn_timing_dump") or os.environ.get("VVB200_LIB", "").find("_T") >= 0:

@@ -193,12 +193,26 @@ static int pick_bn(int M, int N, int sms) {
   return c256 <= c128 ? 256 : 128;
 }
 
+// VVB200_GEMM_PAIR=0 keeps every GEMM on the 1-CTA kernel (A/B experiments)
+static bool pair_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("VVB200_GEMM_PAIR");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+// large GEMMs whose N is a multiple of 256 run on the CTA-pair kernel (bn code 512)
+static int pick_tile(int M, int N, int K, int sms) {
+  if (pair_enabled() && N % 256 == 0 && K % 64 == 0 && M >= 1024) return 512;
+  return pick_bn(M, N, sms);
+}
+
 static GemmOp make_op(vv_engine* e, const bf16* A, int lda, int a_rows, int M, const bf16* Bw, int ldb, int N, int K) {
   GemmOp op;
   op.s.M = M; op.s.N = N; op.s.K = K;
-  op.bn = pick_bn(M, N, e->num_sms);
+  op.bn = pick_tile(M, N, K, e->num_sms);
   op.tA = make_tmap_bf16(A, a_rows, K, lda, 128);
-  op.tB = make_tmap_bf16(Bw, N, K, ldb, op.bn);
+  op.tB = make_tmap_bf16(Bw, N, K, ldb, op.bn == 512 ? 128 : op.bn);
   return op;
 }
 static GemmOp make_conv_op(vv_engine* e, const bf16* X, int ldx, int a_rows, int M, const bf16* Wt, int groups, int taps) {
@@ -211,6 +225,10 @@ static GemmOp make_conv_op(vv_engine* e, const bf16* X, int ldx, int a_rows, int
   return op;
 }
 static inline void run_gemm(vv_engine* e, const GemmOp& op, const GemmEpi& epi) {
+  if (op.bn == 512 && !gemm_pair_supported(op.s, epi)) {
+    fprintf(stderr, "vvb200: GEMM planned for the CTA-pair kernel has an unsupported epilogue/shape\n");
+    abort();
+  }
   launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st);
   e->launches++;
 }
@@ -1332,14 +1350,17 @@ extern "C" int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* Bw
                             const vv_gemm_epilogue* epi, int bn) {
   if (!e || !A || !Bw || M <= 0 || N <= 0 || K <= 0 || (K % 64) || (lda % 8) || (ldb % 8))
     return fail(VV_ERR_ARG, "vv_gemm_bf16: bad argument (K %% 64 == 0, ld %% 8 == 0 required)");
-  if (bn != 64 && bn != 128 && bn != 256) bn = pick_bn(M, N, e->num_sms);
+  if (bn != 64 && bn != 128 && bn != 256 && bn != 512) bn = pick_tile(M, N, K, e->num_sms);
   CK(cudaSetDevice(e->device));
   GemmOp op;
   op.s.M = M; op.s.N = N; op.s.K = K;
   op.bn = bn;
+  const GemmEpi ge = to_epi(e, epi);
+  if (bn == 512 && !gemm_pair_supported(op.s, ge))
+    return fail(VV_ERR_ARG, "vv_gemm_bf16: bn=512 (CTA pair) needs N %% 256 == 0 and 16-byte aligned bias/gate");
   op.tA = make_tmap_bf16(A, M, K, lda, 128);
-  op.tB = make_tmap_bf16(Bw, N, K, ldb, bn);
-  run_gemm(e, op, to_epi(e, epi));
+  op.tB = make_tmap_bf16(Bw, N, K, ldb, bn == 512 ? 128 : bn);
+  run_gemm(e, op, ge);
   CKL();
   return 0;
 }

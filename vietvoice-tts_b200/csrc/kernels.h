@@ -42,7 +42,12 @@ struct GemmShape {
 // 2-D bf16 tensor map, 128B swizzle, box = {64 columns, box_rows rows}
 CUtensorMap make_tmap_bf16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 
-// bn in {64,128,256}; tmA box rows 128, tmB box rows bn.
+// bn in {64,128,256}: 1-CTA kernel, tmA box rows 128, tmB box rows bn.
+// bn == 512: CTA-pair kernel (256 x 256 tile per 2-CTA cluster, tcgen05 cta_group::2), tmA and tmB box rows 128;
+//            only when gemm_pair_supported(s, e).
+bool gemm_pair_supported(const GemmShape& s, const GemmEpi& e);
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
+                      int num_sms, cudaStream_t st);
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
                  int num_sms, cudaStream_t st);
 
