@@ -71,9 +71,8 @@ if what in ("gemm", "all"):
                 lib.vv_gemm_timing_dump()
 torch.cuda.synchronize()
 lib.vv_engine_destroy(h)
-if hasattr(lib, "vv_attn_timing_dump") or os.environ.get("VVB200_LIB", "").find("_T") >= 0:
-    try:
-        import ctypes
-        ctypes.CDLL(os.environ["VVB200_LIB"]).vv_attn_timing_dump()
-    except Exception as exc:
-        print("no timing dump:", exc)
+if what in ("attn", "all"):
+    name = "vv_attn_timing_dump3" if os.environ.get("VVB200_ATTN") == "3" else "vv_attn_timing_dump"
+    if hasattr(lib, name):
+        sys.stdout.flush()
+        getattr(lib, name)()

@@ -360,7 +360,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 }
 
 #if VV_ATTN_TIMING
-extern "C" void vv_attn_timing_dump() {
+extern "C" void vv_attn2_timing_dump() {
   long long h[8];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_attn_timing, sizeof(h));
@@ -373,7 +373,7 @@ extern "C" void vv_attn_timing_dump() {
 }
 #endif
 
-void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
+void launch_attention2(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM);

@@ -1,0 +1,380 @@
+// Non-causal flash attention for sm_100a (d_h = 64), tcgen05 + TMEM — version 3: one 128-row query tile per CTA,
+// TWO CTAs resident per SM (256 TMEM columns, ~82 KB smem, 256 threads each).
+//
+// At d_h = 64 this op is bound by the exponential, not the tensor pipe: a 128x128 score tile costs 512 tensor cycles
+// (QK^T + PV) but 1024 MUFU cycles (16 ex2/clk/SM).  The v2 kernel (attn.cu: two tiles per CTA, one CTA per SM) ran the
+// MUFU pipe at ~49 %: both softmax warpgroups moved through their phases in lock step and every CTA paid its Q/K load
+// latency and its O store with the SM otherwise idle.  Here the two tiles of an SM belong to independent CTAs: their
+// phases drift apart, one CTA's prologue/epilogue runs under the other's main loop, and the row maximum is no longer a
+// separate pass —
+//   * softmax uses the running reference maximum m_ref of the previous kv tiles (lazy rescale, tau = 8): the exp2 loop
+//     starts right after the TMEM load and tracks the new row maximum on the ALU pipe while the MUFU pipe does exp2;
+//   * only if some row's maximum grew by more than tau (rare after the first tile) the warp redoes the tile's exp2 with
+//     the new reference and rescales O.
+//   S = Q K^T : tcgen05.mma M128 N128 K64 -> TMEM cols [0,128)
+//   P (bf16)  : tcgen05.st -> TMEM cols [128,192); O += P V : tcgen05.mma M128 N64 K128, A from TMEM, V MN-major
+//               straight from the TMA tile; O in TMEM cols [192,256)
+// RoPE has already been applied to q/k by the QKV GEMM epilogue.
+//
+// Replaces the attention sub-graph of `transformer.onnx` (/root/reference/vietvoicetts/core/tts_engine.py:161-172).
+#include "kernels.h"
+#include "ptx.cuh"
+#include "attn_softmax.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+
+#ifndef VV_ATTN_SKEW
+#define VV_ATTN_SKEW 1100    // cycles by which the second CTA of an SM is held back in the first wave (0 = off)
+#endif
+#ifndef VV_ATTN_TIMING
+#define VV_ATTN_TIMING 0
+#endif
+#if VV_ATTN_TIMING
+#define TICK(i) do { long long _t = clock64(); tacc[i] += _t - tlast; tlast = _t; } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
+
+namespace vv {
+
+#if VV_ATTN_TIMING
+__device__ unsigned long long g_attn3_timing[10];
+#endif
+
+namespace attn3 {
+constexpr int K_STAGES = 2;
+constexpr int V_STAGES = 2;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
+constexpr int Q_OFF = 0;
+constexpr int K_OFF = Q_OFF + TILE_BYTES;
+constexpr int V_OFF = K_OFF + K_STAGES * TILE_BYTES;
+constexpr int BAR_OFF = V_OFF + V_STAGES * TILE_BYTES;
+constexpr int SMEM = BAR_OFF + 256 + 1024;
+constexpr int THREADS = 256;   // 2 full warpgroups (setmaxnreg is warpgroup-aligned): softmax | TMA, MMA, 2 idle warps
+constexpr uint32_t TM_S = 0;
+constexpr uint32_t TM_P = 128;
+constexpr uint32_t TM_O = 192;
+constexpr uint32_t TM_COLS = 256;
+constexpr float TAU = 8.0f;
+}  // namespace attn3
+
+__global__ void __launch_bounds__(attn3::THREADS, 2)
+attn3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  using namespace attn3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // K_STAGES
+  uint64_t* k_empty = k_full + K_STAGES;
+  uint64_t* v_full = k_empty + K_STAGES;   // V_STAGES
+  uint64_t* v_empty = v_full + V_STAGES;
+  uint64_t* s_full = v_empty + V_STAGES;   // S(j) accumulator complete             (MMA -> softmax)
+  uint64_t* s_free = s_full + 1;           // S(j) copied to registers               (softmax -> MMA)
+  uint64_t* p_full = s_free + 1;           // P(j) in TMEM, O rescaled               (softmax -> MMA)
+  uint64_t* pv_done = p_full + 1;          // O += P(j) V(j) complete                (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x % p.n_tiles;
+  const int head = blockIdx.x / p.n_tiles;
+  const int seq = p.tile_seq[tile];
+  const int q0 = p.tile_q0[tile];
+  const int seq_row0 = p.seq_off[seq];
+  const int kv_len = p.seq_len[seq];
+  const int n_kv = (kv_len + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < K_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < V_STAGES; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, TM_COLS);
+#if VV_ATTN_SKEW > 0
+  // The two CTAs of an SM share one MUFU pipe.  Started together they run their exp2 phases at the same time (each at
+  // half rate) and then both leave the pipe idle; offset by about half an iteration they alternate.  All CTAs of a
+  // launch take the same time per kv tile, so the offset set up in the first wave persists through later waves.
+  const bool first_wave = p.sm_resident != nullptr && blockIdx.x < 2 * p.num_sms;
+  if (first_wave) {
+    if (threadIdx.x == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const int prev = atomicAdd(p.sm_resident + smid, 1);
+      if (prev & 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < VV_ATTN_SKEW) {
+        }
+      }
+    }
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4) {
+    setmaxnreg_dec<48>();       // 128 x 208 + 128 x 48 = 256 x 128 registers: two such CTAs fill the SM's register file
+    if (warp == 4) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(smem + Q_OFF, &tmQKV, head * 64, seq_row0 + q0, q_full);
+        int ks = 0, vs = 0;
+        uint32_t kph = 0, vph = 0;
+        for (int j = 0; j < n_kv; ++j) {
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_expect_tx(&k_full[ks], TILE_BYTES);
+          tma_load_2d(smem + K_OFF + ks * TILE_BYTES, &tmQKV, p.dim + head * 64, seq_row0 + j * 128, &k_full[ks]);
+          if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_expect_tx(&v_full[vs], TILE_BYTES);
+          tma_load_2d(smem + V_OFF + vs * TILE_BYTES, &tmQKV, 2 * p.dim + head * 64, seq_row0 + j * 128, &v_full[vs]);
+          if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+        }
+      }
+    } else if (warp == 5) {
+      // ------------------------------------------------------------------ MMA issuer.  S(n+1) is issued as soon as the
+      // softmax warps have copied S(n) to registers, i.e. it runs under softmax(n).
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 1);
+        const uint32_t q_addr = smem_u32(smem + Q_OFF);
+        const uint32_t k_addr = smem_u32(smem + K_OFF);
+        const uint32_t v_addr = smem_u32(smem + V_OFF);
+        const uint32_t d_s = tmem_base + TM_S;
+        const uint32_t d_o = tmem_base + TM_O;
+        mbar_wait(q_full, 0);
+        int ks = 0, vs = 0;
+        uint32_t kph = 0, vph = 0;
+        for (int n = 0; n <= n_kv; ++n) {
+          if (n < n_kv) {
+            if (n > 0) mbar_wait(s_free, (n - 1) & 1);
+            mbar_wait(&k_full[ks], kph);
+            tc_fence_after();
+            const uint64_t a0 = make_sdesc_sw128(q_addr);
+            const uint64_t b0 = make_sdesc_sw128(k_addr + ks * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d_s, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+            umma_commit(s_full);
+            umma_commit(&k_empty[ks]);
+            if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+          }
+          if (n > 0) {
+            mbar_wait(p_full, (n - 1) & 1);
+            mbar_wait(&v_full[vs], vph);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t b = make_sdesc_sw128(v_addr + vs * TILE_BYTES + k * 2048);
+              umma_ts(d_o, tmem_base + TM_P + k * 8, b, idesc_o, !(n == 1 && k == 0));
+            }
+            umma_commit(pv_done);
+            umma_commit(&v_empty[vs]);
+            if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup: thread = query row
+    setmaxnreg_inc<208>();
+
+    const int r = threadIdx.x;                 // row within tile == TMEM lane
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const uint32_t ts = tmem_base + lane_base + TM_S;
+    const uint32_t tp = tmem_base + lane_base + TM_P;
+    const uint32_t to = tmem_base + lane_base + TM_O;
+    float m_ref = 0.0f, l = 0.0f;
+#if VV_ATTN_TIMING
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      TICK(0);   // wait S
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                     // S may be overwritten by S(j+1) from here on
+      TICK(1);   // tmem ld
+      const int kv_valid = kv_len - j * 128;
+      const bool partial = kv_valid < 128;     // warp-uniform: last kv tile of a sequence whose length is not k*128
+      if (j == 0) {
+        // first tile: no reference yet -> plain row maximum (4 independent 3-input chains)
+        if (partial) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+        }
+        float mxa = __uint_as_float(s[0]), mxb = __uint_as_float(s[1]), mxc = __uint_as_float(s[2]),
+              mxd = __uint_as_float(s[3]);
+#pragma unroll
+        for (int i = 4; i < 124; i += 8) {
+          mxa = fmax3(mxa, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+          mxb = fmax3(mxb, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          mxc = fmax3(mxc, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+          mxd = fmax3(mxd, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+        }
+        mxa = fmax3(mxa, __uint_as_float(s[124]), __uint_as_float(s[125]));
+        mxb = fmax3(mxb, __uint_as_float(s[126]), __uint_as_float(s[127]));
+        m_ref = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
+      }
+      TICK(2);   // first-tile max
+      float sum, mx;
+      if (partial) softmax_row<true, true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, mx);
+      else softmax_row<true, false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, mx);
+      mx *= p.scale_log2;
+      TICK(3);   // exp2 + max tracking + pack + P store
+      if (j > 0 && __any_sync(0xffffffffu, (mx - m_ref) > TAU)) {
+        // some row of this warp outgrew the reference: redo this tile against the new maximum, rescale O and l
+        const float m_new = fmaxf(m_ref, mx);
+        const float f = fast_exp2(m_ref - m_new);
+        m_ref = m_new;
+        float dummy;
+        tmem_st_wait();                        // first-pass P stores retired before the same columns are rewritten
+        if (partial) softmax_row<false, true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum, dummy);
+        else softmax_row<false, false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum, dummy);
+        l *= f;
+        uint32_t o[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(to + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st32(to + c * 32, o);
+        }
+#if VV_ATTN_TIMING
+        tacc[8] += 1;
+#endif
+      }
+      TICK(4);   // redo (reference outgrown)
+      tmem_st_wait();
+      l += sum;
+      tc_fence_before();
+      mbar_arrive(p_full);
+      TICK(6);   // O rescale + P store + arrive
+    }
+    // ---- finalize: O / l -> bf16
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int qrow = q0 + r;
+    const float inv = 1.0f / l;
+    bf16* orow = p.out + (size_t)(seq_row0 + qrow) * p.dim + head * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(to + c * 32, o);
+      tmem_ld_wait();
+      if (qrow < kv_len) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {   // 2 x 256-bit stores: whole 32-byte sectors per instruction
+          uint4 u0, u1;
+          u0.x = pack_bf16(__uint_as_float(o[16 * g]) * inv, __uint_as_float(o[16 * g + 1]) * inv);
+          u0.y = pack_bf16(__uint_as_float(o[16 * g + 2]) * inv, __uint_as_float(o[16 * g + 3]) * inv);
+          u0.z = pack_bf16(__uint_as_float(o[16 * g + 4]) * inv, __uint_as_float(o[16 * g + 5]) * inv);
+          u0.w = pack_bf16(__uint_as_float(o[16 * g + 6]) * inv, __uint_as_float(o[16 * g + 7]) * inv);
+          u1.x = pack_bf16(__uint_as_float(o[16 * g + 8]) * inv, __uint_as_float(o[16 * g + 9]) * inv);
+          u1.y = pack_bf16(__uint_as_float(o[16 * g + 10]) * inv, __uint_as_float(o[16 * g + 11]) * inv);
+          u1.z = pack_bf16(__uint_as_float(o[16 * g + 12]) * inv, __uint_as_float(o[16 * g + 13]) * inv);
+          u1.w = pack_bf16(__uint_as_float(o[16 * g + 14]) * inv, __uint_as_float(o[16 * g + 15]) * inv);
+          stg256_u(orow + c * 32 + g * 16, u0, u1);
+        }
+      }
+    }
+#if VV_ATTN_TIMING
+    TICK(7);   // final wait + O store
+    tacc[9] = n_kv;
+    if (lane == 0 && blockIdx.x % 97 == 0)
+      for (int i = 0; i < 10; ++i) atomicAdd(&g_attn3_timing[i], (unsigned long long)tacc[i]);
+#endif
+  }
+#if VV_ATTN_TIMING
+  if (warp < 4) {
+    // (softmax threads only; tacc lives in their scope)
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, TM_COLS);
+#if VV_ATTN_SKEW > 0
+  if (first_wave && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicSub(p.sm_resident + smid, 1);     // net zero per launch: no reset needed between launches
+  }
+#endif
+}
+
+void launch_attention3(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM);
+    attr_set = true;
+  }
+  if (p.n_tiles <= 0) return;
+  attn3_kernel<<<p.n_tiles * p.heads, attn3::THREADS, attn3::SMEM, st>>>(tmQKV, p);
+}
+
+#if VV_ATTN_TIMING
+extern "C" void vv_attn_timing_dump3() {
+  unsigned long long h[10];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_attn3_timing, sizeof(h));
+  const char* names[8] = {"wait_S", "tmem_ld", "mask/first max", "exp2+max+pack", "redo", "wait_PV", "P store+arrive",
+                          "final+O store"};
+  double tot = 0;
+  for (int i = 0; i < 8; ++i) tot += double(h[i]);
+  for (int i = 0; i < 8; ++i)
+    printf("  %-16s %14llu  %5.1f%%  %8.0f cyc/kv-iter\n", names[i], h[i], 100.0 * double(h[i]) / (tot + 1e-9),
+           double(h[i]) / double(h[9] ? h[9] : 1));
+  printf("  redo count %llu of %llu kv iterations (sampled warps); %.0f cycles per kv iteration per warp\n", h[8], h[9],
+         tot / double(h[9] ? h[9] : 1));
+  unsigned long long z[10] = {0};
+  cudaMemcpyToSymbol(g_attn3_timing, z, sizeof(z));
+}
+#endif
+
+void launch_attention2(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
+void launch_attention4(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
+
+// VVB200_ATTN=2|4 selects another kernel generation for A/B runs (default: 3 — two free-running CTAs per SM; 2 = two
+// tiles per CTA in lock step, 4 = persistent two-lane CTA with an explicit MUFU ping-pong; both measured slower)
+static int attn_version() {
+  static const int v = [] {
+    const char* e = getenv("VVB200_ATTN");
+    return (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 3;
+  }();
+  return v;
+}
+int attn_q_tile() { return attn_version() == 2 ? 256 : 128; }
+void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
+  switch (attn_version()) {
+    case 2: launch_attention2(tmQKV, p, st); break;
+    case 4: launch_attention4(tmQKV, p, st); break;
+    default: launch_attention3(tmQKV, p, st); break;
+  }
+}
+
+}  // namespace vv

@@ -58,12 +58,15 @@ struct AttnParams {
   const int32_t* seq_len;
   const int32_t* tile_seq;
   const int32_t* tile_q0;
-  int n_tiles;        // number of 256-row q tiles
+  int n_tiles;        // number of attn_q_tile()-row q tiles
   int heads;
   int dim;
   bf16* out;
   float scale_log2;   // (1/sqrt(64)) * log2(e)
+  int32_t* sm_resident = nullptr;   // [>= 256] zero-initialised scratch, one counter per SM (v3 first-wave skew); may be null
+  int num_sms = 0;
 };
+int attn_q_tile();    // query rows per tile_q0 entry expected by launch_attention (128; 256 for the v2 kernel)
 void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
 
 // LayerNorm (no affine) + AdaLN modulation: out = LN(x)*(1+scale)+shift -> bf16.  One warp per row.
