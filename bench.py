@@ -115,6 +115,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def roofline_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,6 +279,17 @@ def run_ours(args):
     snr_vs_resident = float(10 * np.log10(np.sum(pcm0.astype(np.float64) ** 2) / (np.sum(d * d) + 1e-30)))
     same = bool(snr_vs_resident > 40.0)     # e2e result == resident result (same seeds; fp atomics in GRN differ)
 
+    # ---- p50 utterance latency (the second half of BASELINE.json's metric): ONE ~10 s utterance through the same
+    # host-buffer call, alone on the GPU (M = 2 x 1517 rows: tile-quantisation bound, not throughput bound)
+    lat_ms = []
+    if rank == 0:
+        for i in range(2 + 7):
+            t0 = time.perf_counter()
+            eng.synthesize_batch(a_np[:1], i_np[:1], [T], nfe=nfe, seed=9527, chunk_keys=keys[:1], pcm_out=o_np[:1])
+            if i >= 2:
+                lat_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+
     # ---- max over ranks
     if dist is not None:
         t = torch.tensor([ms_total, e2e_ms], device="cuda", dtype=torch.float64)
@@ -298,6 +318,7 @@ def run_ours(args):
     e2e_value = total_audio / (e2e_ms * 1e-3)
     h2d = sum(a.nbytes for a in a_np) + sum(t.nbytes for t in i_np)
     d2h = sum(o.nbytes for o in o_np)
+    traffic = roofline_traffic()
 
     line = {
         "metric": "synth audio-sec/sec (inverse RTF)", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -314,8 +335,14 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "vv::gemm_kernel<BN,false> (qkv/out/ffn GEMMs of the 22 DiT blocks)",
                      "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
-                     "peak_source": f"{which} bf16_tflops_sustained", "traffic": None,
+                     "peak_source": f"{which} bf16_tflops_sustained",
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None,
+                     "algorithmic_flops_per_dit_eval": gemm_fl, "launches_per_dit_eval": 4 * arch.depth,
                      "ms_per_dit_eval": gemm_ms},
+        "latency": {"p50_ms": statistics.median(lat_ms) if lat_ms else None, "B": 1, "T": T, "nfe": nfe,
+                    "audio_s": audio_s, "how": "wall clock around vv_synthesize_batch (host PCM in, int16 PCM out), "
+                    "median of 7 after 2 warm-ups, rank 0"},
         "kernels": {
             "gemm_qkv_ms": cls[0], "gemm_out_ms": cls[1], "gemm_ff1_ms": cls[2], "gemm_ff2_ms": cls[3],
             "attention_ms": cls[4], "attention_tflops": attn_tf, "attention_frac_of_peak": attn_tf / sustained,
