@@ -72,7 +72,7 @@ if what in ("gemm", "all"):
 torch.cuda.synchronize()
 lib.vv_engine_destroy(h)
 if what in ("attn", "all"):
-    name = "vv_attn_timing_dump3" if os.environ.get("VVB200_ATTN") == "3" else "vv_attn_timing_dump"
+    name = "vv_attn_timing_dump"
     if hasattr(lib, name):
         sys.stdout.flush()
         getattr(lib, name)()

@@ -1,13 +1,7 @@
-// Softmax inner loop shared by the attention kernels (attn3.cu, attn4.cu).
+// Softmax inner loop of the attention kernel (attn.cu).
 #pragma once
 #include "ptx.cuh"
 
-#ifndef VV_ATTN_POLY_N
-#define VV_ATTN_POLY_N 0     // of every VV_ATTN_POLY_MOD softmax elements, this many take the FMA-pipe exp2
-#endif
-#ifndef VV_ATTN_POLY_MOD
-#define VV_ATTN_POLY_MOD 4
-#endif
 
 namespace vv {
 
@@ -35,10 +29,10 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
       float x0, x1, x2, x3;
       ffma2(x0, x1, val(k), val(k + 1), scale_log2, -m);
       ffma2(x2, x3, val(k + 2), val(k + 3), scale_log2, -m);
-      const float e0 = ((i % VV_ATTN_POLY_MOD) < VV_ATTN_POLY_N) ? poly_exp2(x0) : fast_exp2(x0);
-      const float e1 = (((i + 1) % VV_ATTN_POLY_MOD) < VV_ATTN_POLY_N) ? poly_exp2(x1) : fast_exp2(x1);
-      const float e2 = (((i + 2) % VV_ATTN_POLY_MOD) < VV_ATTN_POLY_N) ? poly_exp2(x2) : fast_exp2(x2);
-      const float e3 = (((i + 3) % VV_ATTN_POLY_MOD) < VV_ATTN_POLY_N) ? poly_exp2(x3) : fast_exp2(x3);
+      const float e0 = fast_exp2(x0);
+      const float e1 = fast_exp2(x1);
+      const float e2 = fast_exp2(x2);
+      const float e3 = fast_exp2(x3);
       if (TRACK) {
         mxa = fmax3(mxa, val(k), val(k + 1));
         mxb = fmax3(mxb, val(k + 2), val(k + 3));

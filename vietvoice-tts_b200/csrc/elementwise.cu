@@ -1,6 +1,7 @@
 // Bandwidth-bound row kernels of the DiT step: LayerNorm + AdaLN modulation (fp32 residual stream -> bf16 GEMM
 // operand), CFG combine + Euler update, and small fp32 helpers used once per engine / per utterance.
 #include "kernels.h"
+#include <stdlib.h>
 #include "ptx.cuh"
 
 namespace vv {
@@ -15,8 +16,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int VEC4_PER_LANE, bool AFFINE>
 __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, int rows, int dim, const float* __restrict__ a, const float* __restrict__ b,
-          float eps, bf16* __restrict__ out_bf16, float* __restrict__ out_f32) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+          float eps, bf16* __restrict__ out_bf16, float* __restrict__ out_f32, int reverse) {
+  // reverse: walk the rows from the end.  The GEMM that produced x wrote its last row blocks last, so those are the
+  // lines still resident in the 126 MB L2; reading them first turns part of the 4 B/element read into L2 hits, and the
+  // bf16 rows written last here (the lowest ones) are the first ones the next GEMM's TMA asks for.
+  const int blk = reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int row = blk * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * dim);
@@ -68,13 +73,17 @@ static void launch_ln_any(const float* x, int rows, int dim, const float* a, con
                           float* of, cudaStream_t st) {
   const int grid = (rows + 7) / 8;
   if (grid == 0) return;
+  static const int rev = [] {   // VVB200_LN_REVERSE=0: ascending row order (A/B runs)
+    const char* v = getenv("VVB200_LN_REVERSE");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
   switch (dim / 128) {
-    case 1: ln_kernel<1, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
-    case 2: ln_kernel<2, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
-    case 4: ln_kernel<4, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
-    case 8: ln_kernel<8, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
-    case 12: ln_kernel<12, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
-    case 16: ln_kernel<16, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of); break;
+    case 1: ln_kernel<1, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 2: ln_kernel<2, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 4: ln_kernel<4, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 8: ln_kernel<8, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 12: ln_kernel<12, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 16: ln_kernel<16, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
     default: break;  // validated by the engine: dim in {128,256,512,1024,1536,2048}
   }
 }

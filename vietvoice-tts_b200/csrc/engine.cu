@@ -91,7 +91,6 @@ struct vv_engine {
   float2* fft_tw = nullptr;
   float* hann = nullptr;
   float* pos_table = nullptr;
-  int32_t* sm_resident = nullptr;   // per-SM scratch counters of the attention kernel (always back to zero after a launch)
   std::map<int, ModTable> mod;
   // bf16 weights
   bf16 *in_n = nullptr, *in_c = nullptr, *c1 = nullptr, *c2 = nullptr, *out_w = nullptr;
@@ -320,7 +319,6 @@ extern "C" int vv_engine_create(const vv_arch* arch, int device, void* stream, v
   }
   {
     int r = build_tables(e);
-    if (!r) r = dev_alloc(e->allocs, &e->sm_resident, 1024);
     if (r) {
       vv_engine_destroy(e);
       return r;
@@ -812,7 +810,6 @@ static void run_attention(vv_batch* b) {
   p.seq_off = b->seq_off_d; p.seq_len = b->seq_len_d; p.tile_seq = b->tile_seq_d; p.tile_q0 = b->tile_q0_d;
   p.n_tiles = b->n_tiles; p.heads = e->a.heads; p.dim = e->a.dim; p.out = b->attn_o;
   p.scale_log2 = (1.0f / sqrtf((float)e->a.head_dim)) * 1.4426950408889634f;
-  p.sm_resident = e->sm_resident; p.num_sms = e->num_sms;
   launch_attention(b->tQKV, p, e->st);
   e->launches++;
 }
@@ -1404,7 +1401,6 @@ extern "C" int vv_attention_bf16(vv_engine* e, const void* qkv, void* out, int t
   p.seq_off = so; p.seq_len = sl; p.tile_seq = tsd; p.tile_q0 = tqd; p.n_tiles = (int)ts.size();
   p.heads = heads; p.dim = dim; p.out = reinterpret_cast<bf16*>(out);
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  p.sm_resident = e->sm_resident; p.num_sms = e->num_sms;
   launch_attention(tm, p, e->st);
   e->launches++;
   cudaError_t r = cudaStreamSynchronize(e->st);

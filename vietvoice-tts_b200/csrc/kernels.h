@@ -63,10 +63,8 @@ struct AttnParams {
   int dim;
   bf16* out;
   float scale_log2;   // (1/sqrt(64)) * log2(e)
-  int32_t* sm_resident = nullptr;   // [>= 256] zero-initialised scratch, one counter per SM (v3 first-wave skew); may be null
-  int num_sms = 0;
 };
-int attn_q_tile();    // query rows per tile_q0 entry expected by launch_attention (128; 256 for the v2 kernel)
+int attn_q_tile();    // query rows per tile_q0 entry expected by launch_attention (128)
 void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
 
 // LayerNorm (no affine) + AdaLN modulation: out = LN(x)*(1+scale)+shift -> bf16.  One warp per row.

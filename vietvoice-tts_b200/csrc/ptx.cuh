@@ -316,19 +316,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax for 2^f
-// (max rel. error 1.0e-4 — 40x below bf16 resolution), exponent re-attached with an integer add.  Used for a fraction of
-// the softmax elements so that the MUFU pipe (16 ex2/clk/SM) is not the only unit doing exponentials.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;            // 1.5 * 2^23: low mantissa bits now hold round(x)
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05500871316f, 0.24221068621f);
-  p = fmaf(p, f, 0.69328290224f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
