@@ -192,7 +192,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #endif
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
-      TICK(0);   // wait S
+#if VV_ATTN_TIMING
+      { long long _t = clock64(); tacc[j == 0 ? 0 : 5] += _t - tlast; tlast = _t; }   // wait S: first tile | later tiles
+#endif
       tc_fence_after();
       uint32_t s[128];
 #pragma unroll
@@ -318,7 +320,7 @@ extern "C" void vv_attn_timing_dump() {
   unsigned long long h[10];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_attn_timing, sizeof(h));
-  const char* names[8] = {"wait_S", "tmem_ld", "mask/first max", "exp2+max+pack", "redo", "wait_PV", "P store+arrive",
+  const char* names[8] = {"wait_S (j=0)", "tmem_ld", "mask/first max", "exp2+max+pack", "redo", "wait_S (j>0)", "P store+arrive",
                           "final+O store"};
   double tot = 0;
   for (int i = 0; i < 8; ++i) tot += double(h[i]);

@@ -253,11 +253,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < STG_COLS / 4; ++j) {
             const float4 b = sb[j], gt = sg[j];
-            float4 v;
-            v.x = (__uint_as_float(raw[4 * j]) + b.x) * gt.x;
-            v.y = (__uint_as_float(raw[4 * j + 1]) + b.y) * gt.y;
-            v.z = (__uint_as_float(raw[4 * j + 2]) + b.z) * gt.z;
-            v.w = (__uint_as_float(raw[4 * j + 3]) + b.w) * gt.w;
+            float4 v = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                   __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+            fadd2(v.x, v.y, b.x, b.y);
+            fadd2(v.z, v.w, b.z, b.w);
+            fmul2(v.x, v.y, v.x, v.y, gt.x, gt.y);
+            fmul2(v.z, v.w, v.z, v.w, gt.z, gt.w);
             *reinterpret_cast<float4*>(rowp + ((j ^ ((lane >> 1) & 3)) << 4)) = v;   // 64B swizzle
           }
           fence_proxy_async_smem();

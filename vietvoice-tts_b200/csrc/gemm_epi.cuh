@@ -13,6 +13,17 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.0f + t);
 }
+// the same on a pair of values with packed FMUL2 / FFMA2: 5 FMA-pipe issues + 2 MUFU per pair instead of 12 + 2
+__device__ __forceinline__ void gelu_tanh_f2(float& x0, float& x1) {
+  float q0, q1, w0, w1, u0, u1, h0, h1, t0, t1;
+  fmul2(q0, q1, x0, x1, x0, x1);
+  ffma2(w0, w1, q0, q1, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
+  fmul2(u0, u1, w0, w1, x0, x1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  fmul2(h0, h1, x0, x1, 0.5f, 0.5f);
+  ffma2v(x0, x1, h0, h1, t0, t1, h0, h1);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float mish_f(float x) {
   float ex = __expf(fminf(x, 20.0f));
@@ -38,7 +49,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = sb[j];
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        fadd2(v[4 * j], v[4 * j + 1], b.x, b.y);
+        fadd2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
       }
     } else {
 #pragma unroll
@@ -63,7 +75,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int N, int row,
   }
   if (e.act == ACT_GELU_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_tanh_f2(v[j], v[j + 1]);
   } else if (e.act == ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
