@@ -337,6 +337,32 @@ def test_attention_large_logits(eng):
     assert rel_err(out, ref) < 1.5e-2
 
 
+def test_attention_reference_outgrown_by_overflow(eng):
+    """the kernel keeps the first kv tile's row maximum as exp2 reference and only re-references when a tile's row
+    sum exceeds 2^40: here keys of later tiles score hundreds of bits above the first tile (exp2 overflows to inf),
+    then fall back again — the re-reference path, the O / l rescale and the masked tail all have to be exact"""
+    lib, h = eng
+    L, heads = 128 * 4 + 57, 2
+    dim = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(2)
+    qkv = torch.randn(L, 3 * dim, device="cuda", generator=g)
+    qkv[:, dim:2 * dim] *= 0.05                       # tile 0: tiny scores
+    qkv[128:256, dim:2 * dim] *= 400.0                # tile 1: scores ~ +-200 -> far beyond 2^40, partly > 2^127
+    qkv[256:384, dim:2 * dim] *= 40.0                 # tile 2: moderate
+    qkv = qkv.bfloat16()
+    out = torch.zeros(L, dim, device="cuda", dtype=torch.bfloat16)
+    so = (C.c_int32 * 1)(0)
+    sl = (C.c_int32 * 1)(L)
+    _lib.check(lib.vv_attention_bf16(h, P(qkv), P(out), L, so, sl, 1, heads))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().split(dim, dim=-1)
+    ref = torch.nn.functional.scaled_dot_product_attention(
+        q.view(L, heads, 64).transpose(0, 1), k.view(L, heads, 64).transpose(0, 1),
+        v.view(L, heads, 64).transpose(0, 1)).transpose(0, 1).reshape(L, dim)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1.5e-2
+
+
 @pytest.mark.parametrize("dim", [128, 256, 512, 1024])
 def test_ln_modulate(eng, dim):
     lib, h = eng

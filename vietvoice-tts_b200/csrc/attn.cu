@@ -6,9 +6,12 @@
 // (profiles/README.md; the other generations are in the git history):
 //   * two free-running CTAs per SM instead of two tiles per CTA in lock step: the exp2 phases of the two tiles drift
 //     apart and one CTA's Q/K load latency and O store run under the other's main loop (MUFU pipe 49 % -> 65 %);
-//   * lazy row maximum: softmax uses the running reference maximum m_ref of the previous kv tiles (tau = 8); the exp2
-//     loop starts right after the TMEM load and tracks the new maximum with FMNMX3 on the ALU pipe.  Only if a row
-//     outgrew the reference (rare after the first tile) the warp redoes the tile's exp2 and rescales O;
+//   * no running maximum at all after the first kv tile: exp2 runs against the reference m_ref fixed by the first tile.
+//     Scaling by a power of two is exact in floating point, so a stale reference costs no precision as long as nothing
+//     overflows: P (bf16) and the fp32 accumulators l and O have 2^127 of head room.  The row sum the loop computes
+//     anyway is the detector — only if it exceeds 2^40 (a score 40 bits above the reference, or inf) the warp takes
+//     the tile's true maximum as new reference, redoes the tile's exp2 and rescales O and l.  The inner loop is
+//     FFMA2 + 2 MUFU + FADD2 + F2FP per pair of scores, nothing else;
 //   * packed FFMA2 / FADD2 for scale-subtract and the row sum, no compare/select on full tiles (the tail mask is a
 //     separate loop instance), P streamed to TMEM in 16-column groups (attn_softmax.cuh);
 //   * tried and dropped: explicit MUFU ping-pong between two tiles in a persistent CTA (a single softmax warp cannot
@@ -58,7 +61,7 @@ constexpr uint32_t TM_S = 0;
 constexpr uint32_t TM_P = 128;
 constexpr uint32_t TM_O = 192;
 constexpr uint32_t TM_COLS = 256;
-constexpr float TAU = 8.0f;
+constexpr float SUM_LIMIT = 1.099511627776e12f;   // 2^40: row sum of one kv tile against the current reference
 }  // namespace attn
 
 __global__ void __launch_bounds__(attn::THREADS, 2)
@@ -205,8 +208,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       TICK(1);   // tmem ld
       const int kv_valid = kv_len - j * 128;
       const bool partial = kv_valid < 128;     // warp-uniform: last kv tile of a sequence whose length is not k*128
-      if (j == 0) {
-        // first tile: no reference yet -> plain row maximum (4 independent 3-input chains)
+      // exact row maximum of the tile in registers (4 independent 3-input chains); only the first tile of an item and
+      // the rare re-reference path need it
+      auto row_max = [&]() {
         if (partial) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -223,23 +227,23 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         }
         mxa = fmax3(mxa, __uint_as_float(s[124]), __uint_as_float(s[125]));
         mxb = fmax3(mxb, __uint_as_float(s[126]), __uint_as_float(s[127]));
-        m_ref = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
-      }
+        return fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
+      };
+      if (j == 0) m_ref = row_max();           // first tile: no reference yet
       TICK(2);   // first-tile max
-      float sum, mx;
-      if (partial) softmax_row<true, true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, mx);
-      else softmax_row<true, false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, mx);
-      mx *= p.scale_log2;
-      TICK(3);   // exp2 + max tracking + pack + P store
-      if (j > 0 && __any_sync(0xffffffffu, (mx - m_ref) > TAU)) {
-        // some row of this warp outgrew the reference: redo this tile against the new maximum, rescale O and l
-        const float m_new = fmaxf(m_ref, mx);
+      float sum;
+      if (partial) softmax_row<true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
+      else softmax_row<false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
+      TICK(3);   // exp2 + pack + P store
+      if (j > 0 && __any_sync(0xffffffffu, !(sum < SUM_LIMIT))) {
+        // some row of this warp outgrew the reference by more than 2^40 (or overflowed): take the true maximum as the
+        // new reference, redo this tile, rescale O and l
+        const float m_new = fmaxf(m_ref, row_max());
         const float f = fast_exp2(m_ref - m_new);
         m_ref = m_new;
-        float dummy;
         tmem_st_wait();                        // first-pass P stores retired before the same columns are rewritten
-        if (partial) softmax_row<false, true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum, dummy);
-        else softmax_row<false, false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum, dummy);
+        if (partial) softmax_row<true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum);
+        else softmax_row<false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, 0, false, sum);
         l *= f;
         uint32_t o[32];
 #pragma unroll

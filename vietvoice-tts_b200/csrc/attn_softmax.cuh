@@ -6,18 +6,17 @@
 namespace vv {
 
 // exp2 of one 128-wide score row against reference `m`; P goes straight to TMEM as bf16 pairs, 32 elements (16
-// columns) per tcgen05.st, so only one 16-register group of P is live at a time.  Returns the row sum in `sum`, and
-// (TRACK) the maximum of the raw scores in `mx`.  Scale-and-subtract and the row sum use packed FFMA2 / FADD2.
+// columns) per tcgen05.st, so only one 16-register group of P is live at a time.  Returns the row sum in `sum`.
+// Scale-and-subtract and the row sum use packed FFMA2 / FADD2.
 // MASKED: columns >= kv_valid are keys past the end of the sequence (last kv tile only) and count as -inf.  The mask
 // lives inside this variant so that full tiles run a loop without a single compare/select.
 // The P columns are still being read by PV(j-1) when the loop starts: the first two groups are kept in registers
 // and stored after the wait on `pv_bar` (by then PV(j-1) has long retired), the last two are stored as produced.
-template <bool TRACK, bool MASKED>
+template <bool MASKED>
 __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scale_log2, float m, int kv_valid,
-                                            uint32_t tp, uint64_t* pv_bar, uint32_t pv_parity, bool pv_wait, float& sum,
-                                            float& mx) {
+                                            uint32_t tp, uint64_t* pv_bar, uint32_t pv_parity, bool pv_wait,
+                                            float& sum) {
   float sa0 = 0.0f, sa1 = 0.0f, sb0 = 0.0f, sb1 = 0.0f;   // two packed (FADD2) row-sum chains
-  float mxa = __uint_as_float(s[0]), mxb = mxa;           // column 0 is always a valid key
   auto val = [&](int i) { return (MASKED && i >= kv_valid) ? __uint_as_float(0xff800000u) : __uint_as_float(s[i]); };
   uint32_t pk_all[4][16];
 #pragma unroll
@@ -33,10 +32,6 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
       const float e1 = fast_exp2(x1);
       const float e2 = fast_exp2(x2);
       const float e3 = fast_exp2(x3);
-      if (TRACK) {
-        mxa = fmax3(mxa, val(k), val(k + 1));
-        mxb = fmax3(mxb, val(k + 2), val(k + 3));
-      }
       fadd2(sa0, sa1, e0, e1);
       fadd2(sb0, sb1, e2, e3);
       pk[i / 2] = pack_bf16(e0, e1);
@@ -54,7 +49,6 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
     }
   }
   sum = (sa0 + sa1) + (sb0 + sb1);
-  if (TRACK) mx = fmaxf(mxa, mxb);
 }
 
 }  // namespace vv
