@@ -50,14 +50,17 @@ class TTSEngine:
         self.cleanup()
 
     # ------------------------------------------------------------------------------------------ input preparation
-    def _target_duration(self, text: str, rate: float) -> float:
+    def _target_duration(self, text: str, rate: float, speed: Optional[float] = None) -> float:
         n = self.text_processor.calculate_text_length(text, self.config.pause_punctuation)
-        return max(n / rate / self.config.speed, self.config.min_target_duration)
+        return max(n / rate / (self.config.speed if speed is None else speed), self.config.min_target_duration)
 
-    def _prepare_inputs(self, reference_audio_path_or_bytes, reference_text: str,
-                        target_text: str) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]:
-        """-> per chunk (audio int16 [1,1,N], text_ids int32 [1,L], max_duration int64 [1], time_step int32 [1])"""
+    def _prepare_inputs(self, reference_audio_path_or_bytes, reference_text: str, target_text: str,
+                        speed: Optional[float] = None) -> List[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]:
+        """-> per chunk (audio int16 [1,1,N], text_ids int32 [1,L], max_duration int64 [1], time_step int32 [1]).
+        `speed` overrides config.speed for this call only (the reference mutates the shared config per request,
+        api/tts_engine.py:64-69; a per-call value has no such race)."""
         cfg = self.config
+        speed = cfg.speed if speed is None else speed
         cache_key = reference_audio_path_or_bytes if isinstance(reference_audio_path_or_bytes, (str, bytes)) else None
         audio = self.sample_cache.get(cache_key) if cache_key is not None else None
         if audio is None:
@@ -72,7 +75,7 @@ class TTSEngine:
         ref_seconds = n_samples / cfg.sample_rate
         ref_units = self.text_processor.calculate_text_length(reference_text, cfg.pause_punctuation)
         rate = ref_units / ref_seconds if ref_seconds > 0 else 100
-        total = ref_seconds + self._target_duration(target_text, rate)
+        total = ref_seconds + self._target_duration(target_text, rate, speed)
 
         if total <= cfg.max_chunk_duration:
             chunks = [target_text]
@@ -82,8 +85,8 @@ class TTSEngine:
                 raise ValueError(f"Reference audio duration ({ref_seconds:.1f}s) exceeds max chunk duration "
                                  f"({cfg.max_chunk_duration}s)")
             chunks = []
-            for piece in self.text_processor.chunk_text(target_text, max_chars=int(rate * budget * cfg.speed)):
-                dur = self._target_duration(piece, rate)
+            for piece in self.text_processor.chunk_text(target_text, max_chars=int(rate * budget * speed)):
+                dur = self._target_duration(piece, rate, speed)
                 if ref_seconds + dur <= cfg.max_chunk_duration:
                     chunks.append(piece)
                 else:                                                    # still too long: split again, 90 % target
@@ -93,7 +96,7 @@ class TTSEngine:
 
         inputs = []
         for piece in chunks:
-            dur = self._target_duration(piece, rate)
+            dur = self._target_duration(piece, rate, speed)
             frames = ref_frames + int(dur * cfg.sample_rate) // cfg.hop_length + 1
             ids = self.text_processor.text_to_indices([list(reference_text + piece)])
             inputs.append((audio, ids, np.array([frames], dtype=np.int64), np.array([0], dtype=np.int32)))
