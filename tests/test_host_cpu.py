@@ -122,6 +122,22 @@ def test_wav_roundtrip_and_load(tmp_path):
         AudioProcessor.load_audio(b"\x00\x00\x00\x20ftypM4A not a wav", sr)
 
 
+def test_wav_bytes_in_memory_equals_file(tmp_path):
+    """the in-memory WAV is byte-identical to the saved file and parses as 24 kHz mono int16"""
+    import io
+    import wave as wave_mod
+    from vietvoice_tts_b200.host.audio_processor import AudioProcessor
+    pcm = (np.random.default_rng(3).standard_normal(5000) * 8000).astype(np.int16)
+    path = tmp_path / "a.wav"
+    AudioProcessor.save_audio(pcm, str(path), 24000)
+    blob = AudioProcessor.to_wav_bytes(pcm.reshape(1, 1, -1), 24000)
+    assert blob == path.read_bytes()
+    back = AudioProcessor.load_audio(blob, 24000)
+    assert back.dtype == np.int16 and back.size == pcm.size
+    with pytest.raises(ValueError):
+        AudioProcessor.to_wav_bytes(np.zeros(0, np.int16), 24000)
+
+
 def test_prepare_inputs_matches_reference(tp):
     """TTSEngine._prepare_inputs: duration model, chunking and ids vs the reference's own method
     (/root/reference/vietvoicetts/core/tts_engine.py:43-131), goldens from make_host_goldens.py."""

@@ -102,11 +102,12 @@ class AudioProcessor:
         return audio
 
     @staticmethod
-    def save_audio(audio: np.ndarray, file_path: str, sample_rate: int) -> None:
-        """WAVE_FORMAT_EXTENSIBLE ('WAVEX') file, as soundfile.write(..., format='WAVEX') produces for int16"""
+    def to_wav_bytes(audio: np.ndarray, sample_rate: int) -> bytes:
+        """The bytes `save_audio` would put in the file, built in memory: the reference serves
+        `synthesize_to_bytes` by writing a temp file and reading it back
+        (/root/reference/vietvoicetts/client.py:149-172)."""
         if audio.size == 0:
             raise ValueError("Cannot save empty audio.")
-        Path(file_path).parent.mkdir(parents=True, exist_ok=True)
         flat = audio.reshape(-1)
         if flat.dtype != np.int16:
             if np.issubdtype(flat.dtype, np.floating):   # soundfile maps float [-1,1) to int16 full scale
@@ -119,8 +120,15 @@ class AudioProcessor:
         fact = struct.pack("<I", len(flat))
         body = (b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"fact" + struct.pack("<I", 4) + fact +
                 b"data" + struct.pack("<I", len(data)) + data)
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    @staticmethod
+    def save_audio(audio: np.ndarray, file_path: str, sample_rate: int) -> None:
+        """WAVE_FORMAT_EXTENSIBLE ('WAVEX') file, as soundfile.write(..., format='WAVEX') produces for int16"""
+        payload = AudioProcessor.to_wav_bytes(audio, sample_rate)
+        Path(file_path).parent.mkdir(parents=True, exist_ok=True)
         with open(file_path, "wb") as fh:
-            fh.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+            fh.write(payload)
 
     @staticmethod
     def concatenate_with_crossfade(generated_waves: List[np.ndarray], cross_fade_duration: float,

@@ -172,6 +172,13 @@ class TTSEngine:
         except Exception as exc:
             raise RuntimeError(f"Speech synthesis failed: {str(exc)}")
 
+    def synthesize_to_bytes(self, text: str, **voice) -> Tuple[bytes, float]:
+        """-> (WAV file bytes, wall seconds) without the temp-file round trip of the reference's client
+        (/root/reference/vietvoicetts/client.py:149-172); same keyword arguments as `synthesize`."""
+        voice.pop("output_path", None)
+        wave, elapsed = self.synthesize(text, **voice)
+        return self.audio_processor.to_wav_bytes(wave, self.config.sample_rate), elapsed
+
     def validate_configuration(self, reference_audio: Optional[str] = None) -> bool:
         if reference_audio is None:
             return True
