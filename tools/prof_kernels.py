@@ -71,6 +71,8 @@ if what in ("gemm", "all"):
                 lib.vv_gemm_timing_dump()
 torch.cuda.synchronize()
 lib.vv_engine_destroy(h)
+if what in ("attn", "all") and hasattr(lib, "vv_attn_trace_dump"):
+    lib.vv_attn_trace_dump(b"gpurun_out/attn_trace.csv")
 if what in ("attn", "all"):
     name = "vv_attn_timing_dump"
     if hasattr(lib, name):

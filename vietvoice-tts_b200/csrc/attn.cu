@@ -46,6 +46,14 @@ namespace vv {
 #if VV_ATTN_TIMING
 __device__ unsigned long long g_attn_timing[10];
 #endif
+#ifndef VV_ATTN_TRACE
+#define VV_ATTN_TRACE 0
+#endif
+#if VV_ATTN_TRACE
+// exp2-phase trace of every CTA that runs on ONE SM (smid = VV_ATTN_TRACE - 1): (cta, warp, kv tile, start, end)
+__device__ long long g_attn_trace[5 * 16384];
+__device__ int g_attn_trace_n;
+#endif
 
 namespace attn {
 constexpr int K_STAGES = 2;
@@ -231,10 +239,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       };
       if (j == 0) m_ref = row_max();           // first tile: no reference yet
       TICK(2);   // first-tile max
+#if VV_ATTN_TRACE
+      const long long tr0 = clock64();
+#endif
       float sum;
       if (partial) softmax_row<true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
       else softmax_row<false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
       TICK(3);   // exp2 + pack + P store
+#if VV_ATTN_TRACE
+      {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (lane == 0 && smid == VV_ATTN_TRACE - 1) {
+          const int k = atomicAdd(&g_attn_trace_n, 1);
+          if (k < 16384) {
+            g_attn_trace[5 * k] = blockIdx.x; g_attn_trace[5 * k + 1] = warp; g_attn_trace[5 * k + 2] = j;
+            g_attn_trace[5 * k + 3] = tr0; g_attn_trace[5 * k + 4] = clock64();
+          }
+        }
+      }
+#endif
       if (j > 0 && __any_sync(0xffffffffu, !(sum < SUM_LIMIT))) {
         // some row of this warp outgrew the reference by more than 2^40 (or overflowed): take the true maximum as the
         // new reference, redo this tile, rescale O and l
@@ -335,6 +359,25 @@ extern "C" void vv_attn_timing_dump() {
          tot / double(h[9] ? h[9] : 1));
   unsigned long long z[10] = {0};
   cudaMemcpyToSymbol(g_attn_timing, z, sizeof(z));
+}
+#endif
+
+#if VV_ATTN_TRACE
+extern "C" void vv_attn_trace_dump(const char* path) {
+  static long long h[5 * 16384];
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_attn_trace_n, sizeof(n));
+  cudaMemcpyFromSymbol(h, g_attn_trace, sizeof(h));
+  if (n > 16384) n = 16384;
+  FILE* f = fopen(path, "w");
+  if (!f) return;
+  fprintf(f, "cta,warp,kv,start,end\n");
+  for (int i = 0; i < n; ++i)
+    fprintf(f, "%lld,%lld,%lld,%lld,%lld\n", h[5 * i], h[5 * i + 1], h[5 * i + 2], h[5 * i + 3], h[5 * i + 4]);
+  fclose(f);
+  n = 0;
+  cudaMemcpyToSymbol(g_attn_trace_n, &n, sizeof(n));
 }
 #endif
 
