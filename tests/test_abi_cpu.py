@@ -37,3 +37,23 @@ def test_bad_arch_rejected(lib):
     bad.head_dim = 32
     rc = lib.vv_engine_create(C.byref(bad), 0, None, C.byref(h))
     assert rc == -1
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/vvb200.h must compile as C99 and link against the library"""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "vvb200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %d\\n", vv_version(), vv_device_count() >= 0); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "vietvoice-tts_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root}/include", str(src),
+                        "-o", str(exe), f"-L{libdir}", "-lvvb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split()[0] == "100"
