@@ -52,8 +52,11 @@ constexpr int PAR_BYTES = EPI_WARPS * 2 * 32 * 16;      // bias + gate columns p
 constexpr int BAR_BYTES = 512;
 template <bool TMA_EPI>
 struct Cfg {
-  static constexpr int STAGES = TMA_EPI ? 5 : 6;
-  static constexpr int STG_TOTAL = TMA_EPI ? EPI_WARPS * 2 * STG_BYTES : 0;
+  // ONE delta-box staging buffer per epilogue warp: the 16 KB a second buffer would take buy a sixth smem stage, and
+  // the reduce-add GEMMs wait on TMA data, not on their epilogue (measured: out-proj +3.6 %, FFN-down +6 %)
+  static constexpr int STG_BUFS = 1;
+  static constexpr int STAGES = TMA_EPI ? (STG_BUFS == 1 ? 6 : 5) : 6;
+  static constexpr int STG_TOTAL = TMA_EPI ? EPI_WARPS * STG_BUFS * STG_BYTES : 0;
   static constexpr int SMEM = STAGES * STAGE_BYTES + STG_TOTAL + PAR_BYTES + BAR_BYTES + 1024;
 };
 }  // namespace pair
@@ -187,7 +190,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
     float4* sbias = reinterpret_cast<float4*>(par_base) + ew * 64;
     float4* sgate = sbias + 32;
-    uint8_t* stg = stg_base + ew * 2 * STG_BYTES;
+    uint8_t* stg = stg_base + ew * C::STG_BUFS * STG_BYTES;
     const bool wide = ((reinterpret_cast<uintptr_t>(e.resid) | reinterpret_cast<uintptr_t>(e.out_f32) |
                         reinterpret_cast<uintptr_t>(e.out_bf16)) & 31) == 0 &&
                       (e.ld_resid % 8) == 0 && (e.ld_f32 % 8) == 0 && (e.ld_bf16 % 16) == 0;
@@ -238,7 +241,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int q = 0; q < NBOX; ++q, ++g) {
           uint32_t raw[STG_COLS];
           tmem_ld16(tmem_base + (uint32_t(w * 32) << 16) + acc * BN + c0 * 32 + q * STG_COLS, raw);
-          if (lane == 0) tma_store_wait_read<1>();   // the reduce that last read this buffer (2 boxes ago) drained it
+          if (lane == 0) tma_store_wait_read<C::STG_BUFS - 1>();   // the reduce that last read this buffer drained it
           __syncwarp();
           tmem_ld_wait();
           if (q + 1 == NBOX) {                 // accumulator fully copied to registers: hand it back to the MMA warp
@@ -246,7 +249,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
           }
-          uint8_t* buf = stg + (g & 1) * STG_BYTES;
+          uint8_t* buf = stg + (g % C::STG_BUFS) * STG_BYTES;
           uint8_t* rowp = buf + lane * (STG_COLS * 4);
           const float4* sb = sbias + q * (STG_COLS / 4);
           const float4* sg = sgate + q * (STG_COLS / 4);
