@@ -1,7 +1,8 @@
 // CTA-pair bf16 GEMM for sm_100a: a cluster of two CTAs (one TPC) computes a 256 x 256 tile with
 // tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns),
 // so the smem fill traffic per MMA flop drops by a third against the 1-CTA 128x256 kernel in gemm.cu (48 -> 32 KB
-// per 128x256x64 of work) — that kernel is bound by the L2 -> smem (TMA) rate, not by the tensor pipe.
+// per 128x256x64 of work): tensor-pipe activity 58 % -> 81 % under ncu, and — the loop runs at the 1 kW power cap —
+// less energy per flop (profiles/README.md).  Six 32 KB stages per CTA: the ring is latency-bound, depth matters.
 //
 //   warp 0   TMA producer (both CTAs; all transaction bytes are credited to the LEADER CTA's full barrier)
 //   warp 1   MMA issuer (leader CTA only): M 256 x N 256 x K 16 per instruction, accumulators double-buffered in the
