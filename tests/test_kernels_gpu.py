@@ -22,10 +22,17 @@ def eng():
     h = C.c_void_p()
     carch = TINY.to_c()
     torch.cuda.init()
-    st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.vv_engine_create(C.byref(carch), 0, C.c_void_p(st), C.byref(h)))
+    # The engine launches on the stream it is given; a NULL handle (torch's default stream) would make it create its
+    # own non-blocking stream, unordered with the torch ops that fill the operands.  Run torch and the engine on ONE
+    # explicit stream for the whole module.
+    stream = torch.cuda.Stream()
+    prev = torch.cuda.current_stream()
+    torch.cuda.set_stream(stream)
+    _lib.check(lib.vv_engine_create(C.byref(carch), 0, C.c_void_p(stream.cuda_stream), C.byref(h)))
     yield lib, h
+    torch.cuda.synchronize()
     lib.vv_engine_destroy(h)
+    torch.cuda.set_stream(prev)
 
 
 def P(t):
@@ -83,10 +90,13 @@ def test_gemm_persistent_many_tiles(eng):
 # ---------------------------------------------------------------------------------------------- CTA-pair kernel
 @pytest.mark.parametrize("M,N,K", [
     (256, 256, 64), (128, 256, 128), (300, 512, 256), (1000, 1024, 1024), (3034, 3072, 1024), (3034, 1024, 2048),
-    (257, 256, 64 * 7),
+    (257, 256, 64 * 7), (6656, 1024, 128), (24272, 2048, 64),
 ])
 def test_gemm_pair_plain(eng, M, N, K):
-    """bn=512: 256x256 tile on a 2-CTA cluster (tcgen05 cta_group::2); ragged M, rings wrapping, odd pair count"""
+    """bn=512: 256x256 tile on a 2-CTA cluster (tcgen05 cta_group::2); ragged M, rings wrapping, odd pair count.
+    On 74 clusters the last partial wave of tiles is cut into column slices: 4 x 64 columns for (1000, 1024) [16 tiles],
+    (300, 512), (257, 256); 2 x 128 columns for (6656, 1024) [104 tiles] and (24272, 2048) [760 tiles]; none for the
+    3072-column cases [144 tiles]"""
     lib, h = eng
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -114,7 +124,8 @@ def test_gemm_pair_many_tiles_bf16_gelu(eng):
     assert rel_err(out, ref) < 5e-3
 
 
-@pytest.mark.parametrize("M,N,K,masked", [(700, 256, 512, True), (5000, 1024, 1024, False), (24272, 1024, 256, False)])
+@pytest.mark.parametrize("M,N,K,masked", [(700, 256, 512, True), (5000, 1024, 1024, False), (24272, 1024, 256, False),
+                                          (6656, 1024, 192, False)])
 def test_gemm_pair_gate_residual_inplace(eng, M, N, K, masked):
     """x += gate * (A B^T + bias) in place through the TMA-staged residual epilogue (out-proj / ffn-down form)"""
     lib, h = eng

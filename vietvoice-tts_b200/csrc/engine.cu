@@ -62,6 +62,7 @@ struct ModTable {
 
 struct GemmOp {
   CUtensorMap tA, tB;
+  CUtensorMap tBt;          // CTA-pair kernel only: B with 32-row boxes (tail-wave column slices)
   GemmShape s;
   int bn = 128;
 };
@@ -213,6 +214,7 @@ static GemmOp make_op(vv_engine* e, const bf16* A, int lda, int a_rows, int M, c
   op.bn = pick_tile(M, N, K, e->num_sms);
   op.tA = make_tmap_bf16(A, a_rows, K, lda, 128);
   op.tB = make_tmap_bf16(Bw, N, K, ldb, op.bn == 512 ? 128 : op.bn);
+  if (op.bn == 512) op.tBt = make_tmap_bf16(Bw, N, K, ldb, 32);
   return op;
 }
 static GemmOp make_conv_op(vv_engine* e, const bf16* X, int ldx, int a_rows, int M, const bf16* Wt, int groups, int taps) {
@@ -229,7 +231,7 @@ static inline void run_gemm(vv_engine* e, const GemmOp& op, const GemmEpi& epi) 
     fprintf(stderr, "vvb200: GEMM planned for the CTA-pair kernel has an unsupported epilogue/shape\n");
     abort();
   }
-  launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st);
+  launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st, op.bn == 512 ? &op.tBt : nullptr);
   e->launches++;
 }
 
@@ -1360,6 +1362,7 @@ extern "C" int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* Bw
     return fail(VV_ERR_ARG, "vv_gemm_bf16: bn=512 (CTA pair) needs N %% 256 == 0 and 16-byte aligned bias/gate");
   op.tA = make_tmap_bf16(A, M, K, lda, 128);
   op.tB = make_tmap_bf16(Bw, N, K, ldb, bn == 512 ? 128 : bn);
+  if (bn == 512) op.tBt = make_tmap_bf16(Bw, N, K, ldb, 32);
   run_gemm(e, op, ge);
   CKL();
   return 0;

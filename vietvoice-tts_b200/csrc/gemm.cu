@@ -279,11 +279,11 @@ static void launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmS
 }
 
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
-                 int num_sms, cudaStream_t st) {
+                 int num_sms, cudaStream_t st, const CUtensorMap* tmBt) {
   if (s.conv_taps > 0) {
     launch_t<64, true>(tmA, tmB, s, e, num_sms, st);
   } else if (bn == 512) {
-    launch_gemm_pair(tmA, tmB, s, e, num_sms, st);
+    launch_gemm_pair(tmA, tmB, tmBt, s, e, num_sms, st);
   } else if (bn == 256) {
     launch_t<256, false>(tmA, tmB, s, e, num_sms, st);
   } else if (bn == 128) {

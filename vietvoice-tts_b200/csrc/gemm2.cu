@@ -21,6 +21,7 @@
 #include "gemm_epi.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #ifndef VV_GEMM_TIMING
 #define VV_GEMM_TIMING 0
@@ -62,10 +63,36 @@ struct Cfg {
 };
 }  // namespace pair
 
+// Work unit of a cluster.  Units [0, full) are whole 256 x 256 tiles; the tiles of the last, partial wave are cut into
+// `split` column slices of 256 / split columns each, so that the wave's work spreads over all clusters instead of
+// leaving most of them idle for a whole tile time (N = 1024: 380 tiles on 74 clusters = 5.13 waves, run as 5 waves +
+// one quarter-tile wave instead of 6).  Slices of one tile are adjacent units: they run at the same time on
+// neighbouring clusters and share the A rows in L2.
+struct Unit {
+  int m2;       // 256-row block
+  int n0;       // first column
+  int bn;       // columns (256, 128 or 64)
+};
+__device__ __forceinline__ Unit decode_unit(int u, int full, int n_tiles, int split) {
+  int tile = u, sub = 0, bn = pair::BN;
+  if (u >= full) {
+    const int t = u - full;
+    tile = full + t / split;
+    sub = t % split;
+    bn = pair::BN / split;
+  }
+  Unit r;
+  r.m2 = tile / n_tiles;
+  r.n0 = (tile % n_tiles) * pair::BN + sub * bn;
+  r.bn = bn;
+  return r;
+}
+
 template <bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const GemmShape s, const GemmEpi e) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmBt, const GemmShape s,
+                 const GemmEpi e, const int tail_full, const int tail_split) {
   using namespace pair;
   using C = Cfg<TMA_EPI>;
   extern __shared__ uint8_t smem_raw[];
@@ -114,25 +141,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int kiters = s.K / BK;
   const int cid = blockIdx.x >> 1;
   const int ncl = gridDim.x >> 1;
+  const int units = tail_full + (total - tail_full) * tail_split;   // tail_full == total when nothing is split
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       GT_DECL;
-      for (int tile = cid; tile < total; tile += ncl) {
-        const int m2 = tile / n_tiles, n_blk = tile % n_tiles;
-        const int a_row = (2 * m2 + (int)rank) * BM;
-        const int b_row = n_blk * BN + (int)rank * (BN / 2);
+      for (int u = cid; u < units; u += ncl) {
+        const Unit un = decode_unit(u, tail_full, n_tiles, tail_split);
+        const int a_row = (2 * un.m2 + (int)rank) * BM;
+        const int b_row = un.n0 + (int)rank * (un.bn / 2);
+        const int b_boxes = un.bn / 64;                       // 32-row boxes of B per CTA (tail slices only)
+        const uint32_t tx = 2 * (A_BYTES + (un.bn / 2) * BK * 2);
         for (int kb = 0; kb < kiters; ++kb) {
           GT(6);
           mbar_wait(&empty[stage], phase ^ 1);
           GT(7);   // producer waiting for a free smem slot
-          if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full[stage], tx);
           const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
           uint8_t* sA = smem + stage * STAGE_BYTES;
           tma_load_2d_pair(sA, &tmA, kb * BK, a_row, fb);
-          tma_load_2d_pair(sA + A_BYTES, &tmB, kb * BK, b_row, fb);
+          if (un.bn == BN) {
+            tma_load_2d_pair(sA + A_BYTES, &tmB, kb * BK, b_row, fb);
+          } else {
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_2d_pair(sA + A_BYTES + i * (32 * BK * 2), &tmBt, kb * BK, b_row + 32 * i, fb);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -148,12 +183,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       GT_DECL;
-      for (int tile = cid; tile < total; tile += ncl, ++it) {
+      for (int u = cid; u < units; u += ncl, ++it) {
+        const int ubn = decode_unit(u, tail_full, n_tiles, tail_split).bn;
+        const uint32_t idesc = ubn == BN ? make_idesc_bf16(2 * BM, BN)
+                                         : (ubn == BN / 2 ? make_idesc_bf16(2 * BM, BN / 2) : make_idesc_bf16(2 * BM, BN / 4));
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         GT(0);
@@ -185,8 +222,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int w = warp & 3;                  // TMEM lane quadrant
     const int half = (warp - 4) >> 2;        // column half of the tile
     const int ew = warp - 4;
-    constexpr int CH_PER = BN / 64;          // 32-column chunks per epilogue warp (4)
-    const int c0 = half * CH_PER;
     const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
     const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
     float4* sbias = reinterpret_cast<float4*>(par_base) + ew * 64;
@@ -198,14 +233,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t g = 0;                          // running delta-box counter of this warp (staging buffer parity)
     int it = 0;
     GT_DECL;
-    for (int tile = cid; tile < total; tile += ncl, ++it) {
-      const int m2 = tile / n_tiles, n_blk = tile % n_tiles;
+    for (int u = cid; u < units; u += ncl, ++it) {
+      const Unit un = decode_unit(u, tail_full, n_tiles, tail_split);
+      const int m2 = un.m2;
+      const int ch_per = un.bn / 64;           // 32-column chunks per epilogue warp (4; 2 or 1 in tail slices)
+      const int c0 = half * ch_per;
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = (2 * m2 + (int)rank) * BM + w * 32;
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
-      const int nbase = n_blk * BN;
+      const int nbase = un.n0;
       float4 rnext[8];
       const bool has_res = !TMA_EPI && e.resid != nullptr && row_ok;
       auto load_res = [&](int c, float4 (&r)[8]) {
@@ -222,11 +260,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       if (!TMA_EPI) load_res(c0, rnext);
-      {  // stage this warp's bias / gate columns (CH_PER*32 floats each)
+      {  // stage this warp's bias / gate columns (ch_per*32 floats each)
         const int ncol = nbase + c0 * 32 + lane * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + ncol));
-        if (e.gate) g4 = __ldg(reinterpret_cast<const float4*>(e.gate + ncol));
+        if (lane * 4 < ch_per * 32) {
+          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + ncol));
+          if (e.gate) g4 = __ldg(reinterpret_cast<const float4*>(e.gate + ncol));
+        }
         __syncwarp();
         sbias[lane] = b4;
         sgate[lane] = g4;
@@ -237,7 +277,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       GT(4);   // epilogue warp waiting for the accumulator
       tc_fence_after();
       if (TMA_EPI) {
-        constexpr int NBOX = CH_PER * 32 / STG_COLS;     // delta boxes per warp per tile (8)
+        const int NBOX = ch_per * 32 / STG_COLS;         // delta boxes per warp per unit (8; 4 or 2 in tail slices)
 #pragma unroll 1
         for (int q = 0; q < NBOX; ++q, ++g) {
           uint32_t raw[STG_COLS];
@@ -274,13 +314,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
 #pragma unroll 1
-        for (int c = c0; c < c0 + CH_PER; ++c) {
+        for (int c = c0; c < c0 + ch_per; ++c) {
           uint32_t raw[32];
           tmem_ld32(tmem_base + (uint32_t(w * 32) << 16) + acc * BN + c * 32, raw);
           float4 rcur[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
-          if (c + 1 < c0 + CH_PER) load_res(c + 1, rnext);
+          if (c + 1 < c0 + ch_per) load_res(c + 1, rnext);
           tmem_ld_wait();
           if (row_ok)
             epilogue_chunk(e, s.N, row, nbase + c * 32, raw, rcur, sbias + (c - c0) * 8, sgate + (c - c0) * 8, wide);
@@ -320,8 +360,33 @@ static bool reduce_epilogue_ok(const GemmEpi& e) {
          e.ld_f32 % 4 == 0;
 }
 
-void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
-                      int num_sms, cudaStream_t st) {
+// How to cut the tiles of the last, partial wave: the split (1, 2 or 4 column slices per tile) with the smallest
+// estimated wave time; narrower MMAs re-read A from shared memory per column and are charged 10 % / 30 %.
+// VVB200_GEMM_TAIL=0 disables the split (A/B runs).
+void plan_pair_tail(int total, int clusters, int* full, int* split) {
+  static const bool on = [] {
+    const char* v = getenv("VVB200_GEMM_TAIL");
+    return !(v && v[0] == '0');
+  }();
+  *full = total;
+  *split = 1;
+  const int rem = total % clusters;
+  if (!on || rem == 0) return;
+  const float penalty[3] = {1.0f, 1.1f, 1.3f};
+  float best = 0.9f;                        // a split has to promise at least 10 %
+  for (int i = 1; i < 3; ++i) {
+    const int sp = 1 << i;
+    const float cost = float((rem * sp + clusters - 1) / clusters) / float(sp) * penalty[i];
+    if (cost < best - 1e-6f) {
+      best = cost;
+      *split = sp;
+    }
+  }
+  if (*split > 1) *full = total - rem;
+}
+
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBt, const GemmShape& s,
+                      const GemmEpi& e, int num_sms, cudaStream_t st) {
   using namespace pair;
   static bool attr_set = false;
   if (!attr_set) {
@@ -332,13 +397,17 @@ void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
   const int m2_tiles = (s.M + 2 * BM - 1) / (2 * BM);
   const int total = m2_tiles * (s.N / BN);
   int clusters = num_sms / 2;
-  if (clusters > total) clusters = total;
-  if (clusters < 1) return;
+  if (clusters < 1 || total < 1) return;
+  int full = total, split = 1;
+  if (tmBt) plan_pair_tail(total, clusters, &full, &split);
+  const int units = full + (total - full) * split;
+  if (clusters > units) clusters = units;
+  const CUtensorMap& tBt = tmBt ? *tmBt : tmB;
   if (reduce_epilogue_ok(e)) {
     const CUtensorMap tmO = make_tmap_f32_box16x32(e.out_f32, s.M, s.N, e.ld_f32);
-    gemm_pair_kernel<true><<<2 * clusters, 384, Cfg<true>::SMEM, st>>>(tmA, tmB, tmO, s, e);
+    gemm_pair_kernel<true><<<2 * clusters, 384, Cfg<true>::SMEM, st>>>(tmA, tmB, tmO, tBt, s, e, full, split);
   } else {
-    gemm_pair_kernel<false><<<2 * clusters, 384, Cfg<false>::SMEM, st>>>(tmA, tmB, tmA, s, e);
+    gemm_pair_kernel<false><<<2 * clusters, 384, Cfg<false>::SMEM, st>>>(tmA, tmB, tmA, tBt, s, e, full, split);
   }
 }
 

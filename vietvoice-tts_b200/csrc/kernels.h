@@ -46,10 +46,13 @@ CUtensorMap make_tmap_bf16(const void* base, uint64_t rows, uint64_t cols, uint6
 // bn == 512: CTA-pair kernel (256 x 256 tile per 2-CTA cluster, tcgen05 cta_group::2), tmA and tmB box rows 128;
 //            only when gemm_pair_supported(s, e).
 bool gemm_pair_supported(const GemmShape& s, const GemmEpi& e);
-void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
-                      int num_sms, cudaStream_t st);
+// tmBt: the B matrix again with 32-row boxes, for the column slices the last partial wave of tiles is cut into
+//       (nullptr: whole tiles only).
+void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBt, const GemmShape& s,
+                      const GemmEpi& e, int num_sms, cudaStream_t st);
+void plan_pair_tail(int total_tiles, int clusters, int* full_tiles, int* split);
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
-                 int num_sms, cudaStream_t st);
+                 int num_sms, cudaStream_t st, const CUtensorMap* tmBt = nullptr);
 
 // Non-causal attention over packed rows. qkv [rows, 3*dim] bf16 (q | k | v, heads of 64), out [rows, dim] bf16.
 // Sequence s covers rows [seq_off[s], seq_off[s]+seq_len[s]). q-tile list: tile_seq[i], tile_q0[i] (row within seq).
