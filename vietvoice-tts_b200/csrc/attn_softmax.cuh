@@ -3,7 +3,31 @@
 #include "ptx.cuh"
 
 
+#ifndef VV_ATTN_POLY
+#define VV_ATTN_POLY 1      // of every 4 score pairs, this many take the FMA-pipe exp2 instead of MUFU.EX2
+#endif
+
 namespace vv {
+
+// exp2 of a pair on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 magic add,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 1.0e-4, 40x below bf16 resolution), exponent
+// re-attached with an integer shift-add.  Packed: 6 FFMA2 + 4 FMNMX + 2 shift-adds for two elements.
+// The clamp keeps the exponent arithmetic from wrapping: below -125 the result is ~2^-125 (P rounds it to 0 in bf16
+// terms of the row sum), above +126 it is ~2^126, which trips the row-sum overflow detector like MUFU's inf does.
+__device__ __forceinline__ void poly_exp2_pair(float x0, float x1, float& e0, float& e1) {
+  constexpr float MAGIC = 12582912.0f;     // 1.5 * 2^23
+  x0 = fminf(fmaxf(x0, -125.0f), 126.0f);
+  x1 = fminf(fmaxf(x1, -125.0f), 126.0f);
+  float t0, t1, r0, r1, f0, f1, p0, p1;
+  ffma2(t0, t1, x0, x1, 1.0f, MAGIC);      // low mantissa bits of t hold round(x)
+  ffma2(r0, r1, t0, t1, 1.0f, -MAGIC);     // r = round(x)
+  ffma2v(f0, f1, r0, r1, -1.0f, -1.0f, x0, x1);
+  ffma2(p0, p1, f0, f1, 0.05500871316f, 0.24221068621f);
+  ffma2v(p0, p1, p0, p1, f0, f1, 0.69328290224f, 0.69328290224f);
+  ffma2v(p0, p1, p0, p1, f0, f1, 1.0f, 1.0f);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 
 // exp2 of one 128-wide score row against reference `m`; P goes straight to TMEM as bf16 pairs, 32 elements (16
 // columns) per tcgen05.st, so only one 16-register group of P is live at a time.  Returns the row sum in `sum`.
@@ -28,10 +52,20 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
       float x0, x1, x2, x3;
       ffma2(x0, x1, val(k), val(k + 1), scale_log2, -m);
       ffma2(x2, x3, val(k + 2), val(k + 3), scale_log2, -m);
-      const float e0 = fast_exp2(x0);
-      const float e1 = fast_exp2(x1);
-      const float e2 = fast_exp2(x2);
-      const float e3 = fast_exp2(x3);
+      // pair slots 0..3 repeat every 8 elements; the LAST VV_ATTN_POLY slots of each group go to the FMA pipe
+      float e0, e1, e2, e3;
+      if (((i / 4) % 2) * 2 + 0 >= 4 - VV_ATTN_POLY) {
+        poly_exp2_pair(x0, x1, e0, e1);
+      } else {
+        e0 = fast_exp2(x0);
+        e1 = fast_exp2(x1);
+      }
+      if (((i / 4) % 2) * 2 + 1 >= 4 - VV_ATTN_POLY) {
+        poly_exp2_pair(x2, x3, e2, e3);
+      } else {
+        e2 = fast_exp2(x2);
+        e3 = fast_exp2(x3);
+      }
       fadd2(sa0, sa1, e0, e1);
       fadd2(sb0, sb1, e2, e3);
       pk[i / 2] = pack_bf16(e0, e1);
