@@ -99,8 +99,12 @@ struct vv_engine {
   std::vector<LayerW> layers;
   std::vector<ConvNextW> text_blocks, voc_blocks;
   bf16 *voc_embed = nullptr, *voc_head = nullptr;
-  // cached batches for vv_synthesize_batch
+  // cached batches for vv_synthesize_batch, keyed by the frame counts of the chunks.  A batch owns ~1 GB of
+  // activations (B = 8, T = 1500) plus its CUDA graphs, and a request stream produces a new key for nearly every
+  // micro-batch, so the cache is a small LRU (VVB200_BATCH_CACHE entries, default 6), not a map that only grows.
   std::map<std::vector<int64_t>, vv_batch*> batch_cache;
+  std::map<vv_batch*, uint64_t> batch_last_use;
+  uint64_t batch_tick = 0;
 };
 
 struct vv_batch {
@@ -1314,9 +1318,32 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
   if (it != e->batch_cache.end()) {
     b = it->second;
   } else {
-    TRY(vv_batch_create(e, B, key.data(), &b));
+    static const size_t cap = [] {
+      const char* v = getenv("VVB200_BATCH_CACHE");
+      const int n = v ? atoi(v) : 6;
+      return (size_t)(n < 1 ? 1 : n);
+    }();
+    auto evict_lru = [&]() {
+      auto victim = e->batch_cache.end();
+      for (auto c = e->batch_cache.begin(); c != e->batch_cache.end(); ++c)
+        if (victim == e->batch_cache.end() || e->batch_last_use[c->second] < e->batch_last_use[victim->second]) victim = c;
+      if (victim == e->batch_cache.end()) return false;
+      cudaStreamSynchronize(e->st);
+      e->batch_last_use.erase(victim->second);
+      vv_batch_destroy(victim->second);
+      e->batch_cache.erase(victim);
+      return true;
+    };
+    while (e->batch_cache.size() >= cap && evict_lru()) {}
+    int rc = vv_batch_create(e, B, key.data(), &b);
+    while (rc == VV_ERR_CUDA && evict_lru()) {     // out of device memory: drop cached batches until it fits
+      (void)cudaGetLastError();
+      rc = vv_batch_create(e, B, key.data(), &b);
+    }
+    if (rc) return rc;
     e->batch_cache[key] = b;
   }
+  e->batch_last_use[b] = ++e->batch_tick;
   for (int i = 0; i < B; ++i) {
     int64_t rl;
     TRY(vv_preprocess(b, i, reqs[i].audio, reqs[i].n_samples, reqs[i].text_ids, reqs[i].n_ids, reqs[i].noise, seed,
