@@ -82,6 +82,38 @@ def test_bad_arguments_return_errors_not_crashes(setup):
     assert eng.synthesize_batch([audio], [ids], [T])[0].size == (T - (6000 // 256 + 1) - 1) * 256
 
 
+def test_concurrent_callers_share_one_engine(setup):
+    """the reference's REST layer runs requests on worker threads against one engine (api/tts_engine.py:79-87):
+    four threads call the C ABI on the same handle without any Python-side lock; results equal the serial ones"""
+    import threading
+    eng, _ = setup
+    audio = artifact.synthetic_prompt_pcm(6000, 3)
+    ref = 6000 // 256 + 1
+    jobs = [(np.arange(3 + j, dtype=np.int32), [ref + 30 + 7 * j, ref + 50 + 5 * j], 100 + j) for j in range(8)]
+
+    def run(j):
+        ids, T, key = jobs[j]
+        return eng.synthesize_batch([audio, audio], [ids, ids], T, chunk_keys=[key, key + 1000])
+
+    serial = [run(j) for j in range(len(jobs))]
+    got = [None] * len(jobs)
+    errs = []
+
+    def worker(t):
+        try:
+            for j in range(t, len(jobs), 4):
+                got[j] = run(j)
+        except Exception as ex:            # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for a, b in zip(serial, got):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 _CACHE_SCRIPT = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, %r)

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -105,6 +106,9 @@ struct vv_engine {
   std::map<std::vector<int64_t>, vv_batch*> batch_cache;
   std::map<vv_batch*, uint64_t> batch_last_use;
   uint64_t batch_tick = 0;
+  // every public entry point that submits work or touches engine state takes this: callers may share one engine
+  // between threads (the REST layer of the reference runs requests on worker threads, api/tts_engine.py:79-87)
+  std::recursive_mutex mu;
 };
 
 struct vv_batch {
@@ -169,6 +173,7 @@ static int dev_alloc(std::vector<void*>& list, T** out, size_t count, bool zero 
   *out = reinterpret_cast<T*>(p);
   return 0;
 }
+#define ENG_LOCK(e) std::lock_guard<std::recursive_mutex> _eng_lock((e)->mu)
 #define TRY(x)            \
   do {                    \
     int _r = (x);         \
@@ -353,6 +358,7 @@ static_assert(sizeof(BlobEntry) == 152, "blob entry layout");
 
 extern "C" int vv_engine_load_blob(vv_engine* e, const void* blob, size_t nbytes) {
   if (!e || !blob) return fail(VV_ERR_ARG, "vv_engine_load_blob: null argument");
+  ENG_LOCK(e);
   if (e->finalized) return fail(VV_ERR_STATE, "engine already finalized");
   const uint8_t* p = static_cast<const uint8_t*>(blob);
   if (nbytes < 256 || memcmp(p, "VVB200W1", 8) != 0) return fail(VV_ERR_FORMAT, "not a VVB200 weight blob (bad magic)");
@@ -475,6 +481,7 @@ static int build_mod_table(vv_engine* e, int nfe, ModTable** out) {
 
 extern "C" int vv_engine_finalize(vv_engine* e) {
   if (!e) return fail(VV_ERR_ARG, "null engine");
+  ENG_LOCK(e);
   if (e->finalized) return 0;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -552,6 +559,7 @@ extern "C" void vv_engine_destroy(vv_engine* e) {
 // ------------------------------------------------------------------------------------------------ batch
 extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames, vv_batch** out) {
   if (!e || !total_frames || !out || B <= 0) return fail(VV_ERR_ARG, "vv_batch_create: bad argument");
+  ENG_LOCK(e);
   if (!e->finalized) return fail(VV_ERR_STATE, "engine not finalized");
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -732,6 +740,7 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
                              int64_t* ref_len_out) {
   if (!b || !audio || idx < 0 || idx >= b->B || n_ids < 0 || (n_ids > 0 && !text_ids))
     return fail(VV_ERR_ARG, "vv_preprocess: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   if (n_samples < a.n_fft / 2 + 1) return fail(VV_ERR_ARG, "prompt audio too short (%lld samples)", (long long)n_samples);
@@ -882,6 +891,7 @@ static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
 
 extern "C" int vv_sample(vv_batch* b, int nfe, int first_step, int n_steps) {
   if (!b) return fail(VV_ERR_ARG, "null batch");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   CK(cudaSetDevice(e->device));
   for (int i = 0; i < b->B; ++i)
@@ -925,6 +935,7 @@ extern "C" int vv_sample(vv_batch* b, int nfe, int first_step, int n_steps) {
 // debugging / parity aid: input embedding + the first n_layers blocks of step `step`, no Euler update
 extern "C" int vv_debug_partial_step(vv_batch* b, int nfe, int step, int n_layers) {
   if (!b) return fail(VV_ERR_ARG, "null batch");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   CK(cudaSetDevice(e->device));
   if (nfe <= 0) nfe = e->a.nfe;
@@ -942,6 +953,7 @@ extern "C" int vv_debug_partial_step(vv_batch* b, int nfe, int step, int n_layer
 // (nfe-1) DiT steps -> Vocos/iSTFT -> int16 PCM left on the device.  No host<->device copies, no host sync.
 extern "C" int vv_run_resident(vv_batch* b, int nfe) {
   if (!b) return fail(VV_ERR_ARG, "null batch");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -962,6 +974,7 @@ extern "C" int vv_run_resident(vv_batch* b, int nfe) {
 // 7 input-embed GEMM + final projection GEMM + CFG/Euler.  The state (noise) advances by that one step.
 extern "C" int vv_profile_step(vv_batch* b, int nfe, int step, float* ms_out /* [8] */) {
   if (!b || !ms_out) return fail(VV_ERR_ARG, "vv_profile_step: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -1161,6 +1174,7 @@ extern "C" int64_t vv_batch_pcm_len(const vv_batch* b, int idx) {
 
 extern "C" int vv_decode(vv_batch* b, int idx, int16_t* pcm_out, int64_t capacity, int64_t* n_out) {
   if (!b || idx < 0 || idx >= b->B || !pcm_out) return fail(VV_ERR_ARG, "vv_decode: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   CK(cudaSetDevice(e->device));
   TRY(decode_all(b));
@@ -1174,6 +1188,7 @@ extern "C" int vv_decode(vv_batch* b, int idx, int16_t* pcm_out, int64_t capacit
 
 extern "C" int vv_decode_all(vv_batch* b, int16_t* const* pcm_out, int64_t* n_out) {
   if (!b || !pcm_out) return fail(VV_ERR_ARG, "vv_decode_all: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   CK(cudaSetDevice(e->device));
   TRY(decode_all(b));
@@ -1206,6 +1221,7 @@ static int copy_rows_bf16(vv_engine* e, const bf16* src, int ld, int row0, int r
 
 extern "C" int64_t vv_get_tensor(vv_batch* b, int idx, const char* name, float* out, int64_t capacity) {
   if (!b || !name || !out || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_get_tensor: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -1262,6 +1278,7 @@ extern "C" int64_t vv_get_tensor(vv_batch* b, int idx, const char* name, float* 
 
 extern "C" int vv_set_noise(vv_batch* b, int idx, const float* noise) {
   if (!b || !noise || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_set_noise: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -1278,6 +1295,7 @@ extern "C" int vv_set_noise(vv_batch* b, int idx, const float* noise) {
 
 extern "C" int vv_set_ref_len(vv_batch* b, int idx, int64_t ref_len) {
   if (!b || idx < 0 || idx >= b->B || ref_len < 0 || ref_len > b->T[idx]) return fail(VV_ERR_ARG, "vv_set_ref_len: bad argument");
+  ENG_LOCK(b->e);
   b->ref_len[idx] = (int)ref_len;
   b->decoded = false;
   return 0;
@@ -1285,6 +1303,7 @@ extern "C" int vv_set_ref_len(vv_batch* b, int idx, int64_t ref_len) {
 
 extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, const float* cat_mel_text_drop) {
   if (!b || !cat_mel_text || !cat_mel_text_drop || idx < 0 || idx >= b->B) return fail(VV_ERR_ARG, "vv_set_cond: bad argument");
+  ENG_LOCK(b->e);
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   CK(cudaSetDevice(e->device));
@@ -1311,6 +1330,7 @@ extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, cons
 // ------------------------------------------------------------------------------------------------ whole path
 extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed) {
   if (!e || !reqs || B <= 0) return fail(VV_ERR_ARG, "vv_synthesize_batch: bad argument");
+  ENG_LOCK(e);
   std::vector<int64_t> key(B);
   for (int i = 0; i < B; ++i) key[i] = reqs[i].total_frames;
   vv_batch* b = nullptr;
@@ -1379,6 +1399,7 @@ extern "C" int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* Bw
                             const vv_gemm_epilogue* epi, int bn) {
   if (!e || !A || !Bw || M <= 0 || N <= 0 || K <= 0 || (K % 64) || (lda % 8) || (ldb % 8))
     return fail(VV_ERR_ARG, "vv_gemm_bf16: bad argument (K %% 64 == 0, ld %% 8 == 0 required)");
+  ENG_LOCK(e);
   if (bn != 64 && bn != 128 && bn != 256 && bn != 512) bn = pick_tile(M, N, K, e->num_sms);
   CK(cudaSetDevice(e->device));
   GemmOp op;
@@ -1398,6 +1419,7 @@ extern "C" int vv_gemm_bf16(vv_engine* e, const void* A, int lda, const void* Bw
 extern "C" int vv_conv_rows_bf16(vv_engine* e, const void* X, int ldx, const void* Wt, int M, int groups, int taps,
                                  const vv_gemm_epilogue* epi) {
   if (!e || !X || !Wt || M <= 0 || groups <= 0 || taps <= 0 || (ldx % 8)) return fail(VV_ERR_ARG, "vv_conv_rows_bf16: bad argument");
+  ENG_LOCK(e);
   CK(cudaSetDevice(e->device));
   GemmOp op = make_conv_op(e, reinterpret_cast<const bf16*>(X), ldx, M, M, reinterpret_cast<const bf16*>(Wt), groups, taps);
   run_gemm(e, op, to_epi(e, epi));
@@ -1408,6 +1430,7 @@ extern "C" int vv_conv_rows_bf16(vv_engine* e, const void* X, int ldx, const voi
 extern "C" int vv_attention_bf16(vv_engine* e, const void* qkv, void* out, int total_rows, const int32_t* seq_off,
                                  const int32_t* seq_len, int n_seq, int heads) {
   if (!e || !qkv || !out || !seq_off || !seq_len || n_seq <= 0 || heads <= 0) return fail(VV_ERR_ARG, "vv_attention_bf16: bad argument");
+  ENG_LOCK(e);
   CK(cudaSetDevice(e->device));
   const int dim = heads * 64;
   std::vector<int32_t> ts, tq;
@@ -1443,6 +1466,7 @@ extern "C" int vv_attention_bf16(vv_engine* e, const void* qkv, void* out, int t
 extern "C" int vv_ln_modulate(vv_engine* e, const float* x, int rows, int dim, const float* shift, const float* scale,
                               float eps, void* out_bf16) {
   if (!e || !x || !shift || !scale || !out_bf16 || rows <= 0 || dim % 128 || dim > 2048) return fail(VV_ERR_ARG, "vv_ln_modulate: bad argument");
+  ENG_LOCK(e);
   CK(cudaSetDevice(e->device));
   launch_ln_mod(x, rows, dim, shift, scale, eps, reinterpret_cast<bf16*>(out_bf16), e->st);
   e->launches++;
