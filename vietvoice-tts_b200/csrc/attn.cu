@@ -77,6 +77,7 @@ constexpr float SUM_LIMIT = 1.099511627776e12f;   // 2^40: row sum of one kv til
 __global__ void __launch_bounds__(attn::THREADS, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   using namespace attn;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
@@ -124,6 +125,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // prologue done; qkv is the predecessor's output
 
   if (warp >= 4) {
     setmaxnreg_dec<48>();       // 128 x 208 + 128 x 48 = 256 x 128 registers: two such CTAs fill the SM's register file
@@ -342,7 +344,7 @@ void launch_attention_impl(const CUtensorMap& tmQKV, const AttnParams& p, cudaSt
     attr_set = true;
   }
   if (p.n_tiles <= 0) return;
-  attn_kernel<<<p.n_tiles * p.heads, attn::THREADS, attn::SMEM, st>>>(tmQKV, p);
+  launch_k(attn_kernel, p.n_tiles * p.heads, attn::THREADS, attn::SMEM, st, tmQKV, p);
 }
 
 #if VV_ATTN_TIMING

@@ -6,6 +6,10 @@
 
 namespace vv {
 
+static thread_local bool t_pdl = false;
+void pdl_set(bool on) { t_pdl = on; }
+bool pdl_get() { return t_pdl; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -20,9 +24,11 @@ ln_kernel(const float* __restrict__ x, int rows, int dim, const float* __restric
   // reverse: walk the rows from the end.  The GEMM that produced x wrote its last row blocks last, so those are the
   // lines still resident in the 126 MB L2; reading them first turns part of the 4 B/element read into L2 hits, and the
   // bf16 rows written last here (the lowest ones) are the first ones the next GEMM's TMA asks for.
+  pdl_trigger();
   const int blk = reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
   const int row = blk * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * dim);
   float4 v[VEC4_PER_LANE];
@@ -78,12 +84,12 @@ static void launch_ln_any(const float* x, int rows, int dim, const float* a, con
     return (v && v[0] == '0') ? 0 : 1;
   }();
   switch (dim / 128) {
-    case 1: ln_kernel<1, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
-    case 2: ln_kernel<2, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
-    case 4: ln_kernel<4, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
-    case 8: ln_kernel<8, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
-    case 12: ln_kernel<12, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
-    case 16: ln_kernel<16, AFFINE><<<grid, 256, 0, st>>>(x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 1: launch_k(ln_kernel<1, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 2: launch_k(ln_kernel<2, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 4: launch_k(ln_kernel<4, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 8: launch_k(ln_kernel<8, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 12: launch_k(ln_kernel<12, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
+    case 16: launch_k(ln_kernel<16, AFFINE>, grid, 256, 0, st, x, rows, dim, a, b, eps, ob, of, rev); break;
     default: break;  // validated by the engine: dim in {128,256,512,1024,1536,2048}
   }
 }
@@ -101,8 +107,10 @@ void launch_ln_affine(const float* x, int rows, int dim, const float* g, const f
 __global__ void cfg_euler_kernel(float* __restrict__ noise, bf16* __restrict__ nb, int ld_nb,
                                  const float* __restrict__ v, int ldv, const uint8_t* __restrict__ row_mask, int R,
                                  int n_mel, float dt, float cfg) {
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * n_mel) return;
+  pdl_wait();
   const int r = idx / n_mel, c = idx - r * n_mel;
   if (row_mask[r] == 0) return;
   const float vc = v[(size_t)r * ldv + c];
@@ -117,7 +125,7 @@ void launch_cfg_euler(float* noise, bf16* noise_bf16, int ld_nb, const float* v,
                       int R, int n_mel, float dt, float cfg, cudaStream_t st) {
   const int n = R * n_mel;
   if (n == 0) return;
-  cfg_euler_kernel<<<(n + 255) / 256, 256, 0, st>>>(noise, noise_bf16, ld_nb, v, ldv, row_mask, R, n_mel, dt, cfg);
+  launch_k(cfg_euler_kernel, (n + 255) / 256, 256, 0, st, noise, noise_bf16, ld_nb, v, ldv, row_mask, R, n_mel, dt, cfg);
 }
 
 // ---------------------------------------------------------------------------------- small fp32 linear

@@ -829,9 +829,27 @@ static void run_attention(vv_batch* b) {
   e->launches++;
 }
 
+// programmatic dependent launch for the kernels of a DiT evaluation: on for small batches (see kernels.h)
+static bool want_pdl(const vv_batch* b) {
+  static const int forced = [] {
+    const char* v = getenv("VVB200_PDL");
+    return v ? (v[0] == '0' ? 0 : 1) : -1;
+  }();
+  static const int max_rows = [] {
+    const char* v = getenv("VVB200_PDL_MAX_ROWS");
+    return v ? atoi(v) : 8192;
+  }();
+  return forced >= 0 ? forced == 1 : b->M <= max_rows;
+}
+struct PdlScope {
+  explicit PdlScope(bool on) { pdl_set(on); }
+  ~PdlScope() { pdl_set(false); }
+};
+
 // one DiT evaluation (both CFG branches) + Euler update.  n_layers < 0: all layers + final projection.
 static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
   vv_engine* e = b->e;
+  PdlScope pdl(want_pdl(b));
   const vv_arch& a = e->a;
   const int M = b->M, d = a.dim;
   const float *c1b = nullptr, *c2b = nullptr, *outb = nullptr;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
             const GemmEpi e) {
   using C = GemmCfg<BN>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -67,6 +68,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // prologue done; from here on the kernel touches what its predecessor produced
 
   const int m_tiles = (s.M + BM - 1) / BM;
   const int n_tiles = CONV ? s.conv_groups : (s.N + BN - 1) / BN;
@@ -275,7 +277,7 @@ static void launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmS
   int grid = m_tiles * n_tiles;
   if (grid > num_sms) grid = num_sms;
   if (grid < 1) return;
-  gemm_kernel<BN, CONV><<<grid, 384, C::SMEM, st>>>(tmA, tmB, s, e);
+  launch_k(gemm_kernel<BN, CONV>, grid, 384, C::SMEM, st, tmA, tmB, s, e);
 }
 
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,

@@ -95,6 +95,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const GemmEpi e, const int tail_full, const int tail_split) {
   using namespace pair;
   using C = Cfg<TMA_EPI>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + C::STAGES * STAGE_BYTES;
@@ -134,6 +135,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();            // peer barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                    // prologue done; from here on the kernel touches what its predecessor produced
 
   const int m2_tiles = (s.M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = s.N / BN;
@@ -405,9 +407,9 @@ void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   const CUtensorMap& tBt = tmBt ? *tmBt : tmB;
   if (reduce_epilogue_ok(e)) {
     const CUtensorMap tmO = make_tmap_f32_box16x32(e.out_f32, s.M, s.N, e.ld_f32);
-    gemm_pair_kernel<true><<<2 * clusters, 384, Cfg<true>::SMEM, st>>>(tmA, tmB, tmO, tBt, s, e, full, split);
+    launch_k(gemm_pair_kernel<true>, 2 * clusters, 384, Cfg<true>::SMEM, st, tmA, tmB, tmO, tBt, s, e, full, split);
   } else {
-    gemm_pair_kernel<false><<<2 * clusters, 384, Cfg<false>::SMEM, st>>>(tmA, tmB, tmA, tBt, s, e, full, split);
+    launch_k(gemm_pair_kernel<false>, 2 * clusters, 384, Cfg<false>::SMEM, st, tmA, tmB, tmA, tBt, s, e, full, split);
   }
 }
 

@@ -39,6 +39,29 @@ struct GemmShape {
   int conv_groups = 0;
 };
 
+// Launch with programmatic stream serialization (see pdl_wait / pdl_trigger in ptx.cuh) when pdl_set(true) is in
+// effect on this thread, as an ordinary stream-ordered launch otherwise.  Every kernel launched through this MUST call
+// pdl_wait() before its first access to global memory another kernel may write or read.
+// The engine turns it on for small batches only: with few tiles per kernel the launch gap, prologue and pipeline fill
+// of the next kernel are a sizeable part of a 5-20 us kernel and overlap the tail of the current one; at the bench
+// batch (M = 24 272) early-resident dependents cost 2 % instead.  VVB200_PDL=0 / 1 forces it off / on.
+void pdl_set(bool on);
+bool pdl_get();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_get() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 2-D bf16 tensor map, 128B swizzle, box = {64 columns, box_rows rows}
 CUtensorMap make_tmap_bf16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 

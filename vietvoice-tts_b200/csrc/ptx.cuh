@@ -293,6 +293,14 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Programmatic dependent launch.  A kernel launched with the programmatic-serialization attribute (launch_k in
+// kernels.h) may become resident while its predecessor in the stream is still draining: it runs its prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and then blocks in pdl_wait() until the predecessor has
+// completed and its memory is visible.  pdl_trigger() tells the runtime that the NEXT kernel may be scheduled as soon
+// as every CTA of this grid has started.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of work
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
   uint64_t ra, rb, rc, rd;
