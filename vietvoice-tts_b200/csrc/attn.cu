@@ -205,8 +205,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
+    bool s_ready = false;                      // S(j) already seen complete by the probe inside softmax(j-1)
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      if (!s_ready) mbar_wait(s_full, j & 1);
 #if VV_ATTN_TIMING
       { long long _t = clock64(); tacc[j == 0 ? 0 : 5] += _t - tlast; tlast = _t; }   // wait S: first tile | later tiles
 #endif
@@ -247,8 +248,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const long long tr0 = clock64();
 #endif
       float sum;
-      if (partial) softmax_row<true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
-      else softmax_row<false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum);
+      s_ready = false;
+      uint64_t* nb = j + 1 < n_kv ? s_full : nullptr;
+      if (partial)
+        softmax_row<true>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, nb, (j + 1) & 1,
+                          nb ? &s_ready : nullptr);
+      else
+        softmax_row<false>(s, p.scale_log2, m_ref, kv_valid, tp, pv_done, (j - 1) & 1, j > 0, sum, nb, (j + 1) & 1,
+                           nb ? &s_ready : nullptr);
       TICK(3);   // exp2 + pack + P store
 #if VV_ATTN_TRACE
       {

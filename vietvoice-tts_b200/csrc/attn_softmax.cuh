@@ -39,13 +39,18 @@ __device__ __forceinline__ void poly_exp2_pair(float x0, float x1, float& e0, fl
 template <bool MASKED>
 __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scale_log2, float m, int kv_valid,
                                             uint32_t tp, uint64_t* pv_bar, uint32_t pv_parity, bool pv_wait,
-                                            float& sum) {
+                                            float& sum, uint64_t* next_bar = nullptr, uint32_t next_parity = 0,
+                                            bool* next_ready = nullptr) {
   float sa0 = 0.0f, sa1 = 0.0f, sb0 = 0.0f, sb1 = 0.0f;   // two packed (FADD2) row-sum chains
   auto val = [&](int i) { return (MASKED && i >= kv_valid) ? __uint_as_float(0xff800000u) : __uint_as_float(s[i]); };
   uint32_t pk_all[4][16];
+  // both barriers this row will need next are probed early and without blocking (PV(j-1) here, S(j+1) two groups
+  // further down): they completed long ago in the steady state, and the probe's latency runs under the exp2 stream
+  const bool pv_ready = pv_wait ? mbar_test(pv_bar, pv_parity) : true;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t (&pk)[16] = pk_all[c];
+    if (c == 2 && next_ready) *next_ready = mbar_test(next_bar, next_parity);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const int k = c * 32 + i;
@@ -73,7 +78,7 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
     }
     if (c == 1) {
       if (pv_wait) {
-        mbar_wait(pv_bar, pv_parity);          // P buffer free again, O quiescent
+        if (!pv_ready) mbar_wait(pv_bar, pv_parity);   // P buffer free again, O quiescent
         tc_fence_after();
       }
       tmem_st16(tp, pk_all[0]);
