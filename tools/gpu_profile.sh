@@ -14,3 +14,8 @@ timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k re
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:gemm_pair -s 7 -c 1 -f \
     -o gpurun_out/gemm_pair_out $G > gpurun_out/ncu_gemm_out.log 2>&1
 echo "gemm captures rc=$?"
+A="python tools/prof_kernels.py attn 3"
+$A > gpurun_out/plain_attn.log 2>&1 &&
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 2 -c 1 -f \
+    -o gpurun_out/attn_final $A > gpurun_out/ncu_attn_final.log 2>&1
+echo "attention capture rc=$?"
