@@ -270,25 +270,39 @@ def test_gemm_rope_epilogue(eng):
     assert rel_err(out, ref) < 2e-5
 
 
-def test_conv_rows_grouped(eng):
-    """conv_pos_embed as implicit GEMM: grouped Conv1d k=31 over time with zero padding + Mish"""
+@pytest.mark.parametrize("groups,taps,T,extras", [(4, 31, 333, False), (16, 31, 2100, True), (2, 7, 700, False),
+                                                 (3, 33, 257, True), (1, 1, 40, False)])
+def test_conv_rows_grouped(eng, groups, taps, T, extras):
+    """conv_pos_embed as implicit GEMM: grouped Conv1d over time with zero padding + Mish.  The resident-halo kernel
+    (conv.cu) reads tap t through a descriptor advanced by t rows: every tap count / tile count / ragged end here
+    exercises another phase of the 8-row swizzle pattern; `extras` adds the residual, row mask and bf16 output of the
+    second conv of the DiT"""
     lib, h = eng
-    groups, taps, T = 4, 31, 333
     dim = groups * 64
-    g = torch.Generator(device="cuda").manual_seed(9)
+    g = torch.Generator(device="cuda").manual_seed(9 + T)
     x = torch.randn(T, dim, device="cuda", generator=g).bfloat16()
     w = (torch.randn(dim, 64, taps, device="cuda", generator=g) / math.sqrt(64 * taps)).bfloat16()
     bias = torch.randn(dim, device="cuda", generator=g) * 0.1
     # [g][tap][co][ci]
     wt = w.view(groups, 64, 64, taps).permute(0, 3, 1, 2).contiguous().view(groups * taps * 64, 64)
-    out = torch.empty(T, dim, device="cuda")
+    out = torch.full((T + 1, dim), float("nan"), device="cuda")
     ep = _lib.VVGemmEpilogue()
     ep.bias = bias.data_ptr(); ep.act = 3; ep.out_f32 = out.data_ptr(); ep.ld_f32 = dim
-    _lib.check(lib.vv_conv_rows_bf16(h, P(x), dim, P(wt), T, groups, taps, C.byref(ep)))
-    torch.cuda.synchronize()
     ref = torch.nn.functional.conv1d(x.float().t()[None], w.float(), bias, padding=taps // 2, groups=groups)[0].t()
     ref = torch.nn.functional.mish(ref)
-    assert rel_err(out, ref) < 1e-4
+    if extras:
+        res = torch.randn(T, dim, device="cuda", generator=g)
+        mask = (torch.rand(T, device="cuda", generator=g) > 0.1).to(torch.uint8)
+        outb = torch.empty(T, dim, device="cuda", dtype=torch.bfloat16)
+        ep.resid = res.data_ptr(); ep.ld_resid = dim; ep.row_mask = mask.data_ptr()
+        ep.out_bf16 = outb.data_ptr(); ep.ld_bf16 = dim
+        ref = (ref + res) * mask[:, None].float()
+    _lib.check(lib.vv_conv_rows_bf16(h, P(x), dim, P(wt), T, groups, taps, C.byref(ep)))
+    torch.cuda.synchronize()
+    assert rel_err(out[:T], ref) < 1e-4
+    assert torch.isnan(out[T:]).all()                 # nothing written past the last row
+    if extras:
+        assert rel_err(outb, ref) < 4e-3
 
 
 @pytest.mark.parametrize("lens,heads", [([128], 1), ([256], 2), ([100], 4), ([300, 77, 513], 4), ([1501], 16),

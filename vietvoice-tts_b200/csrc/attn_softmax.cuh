@@ -51,6 +51,10 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
   for (int c = 0; c < 4; ++c) {
     uint32_t (&pk)[16] = pk_all[c];
     if (c == 2 && next_ready) *next_ready = mbar_test(next_bar, next_parity);
+    if (MASKED && c * 32 >= kv_valid) {        // whole group past the end of the sequence (warp-uniform): P = 0,
+#pragma unroll                                 // no exp2 issued at all
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    } else
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const int k = c * 32 + i;

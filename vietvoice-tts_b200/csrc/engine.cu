@@ -63,7 +63,8 @@ struct ModTable {
 
 struct GemmOp {
   CUtensorMap tA, tB;
-  CUtensorMap tBt;          // CTA-pair kernel only: B with 32-row boxes (tail-wave column slices)
+  CUtensorMap tBt;          // CTA-pair kernel: B with 32-row boxes (tail-wave column slices);
+                            // conv op: the ACTIVATIONS with 32-row boxes (last piece of the resident halo, conv.cu)
   GemmShape s;
   int bn = 128;
 };
@@ -232,6 +233,7 @@ static GemmOp make_conv_op(vv_engine* e, const bf16* X, int ldx, int a_rows, int
   op.s.conv_taps = taps; op.s.conv_groups = groups;
   op.bn = 64;
   op.tA = make_tmap_bf16(X, a_rows, groups * 64, ldx, 128);
+  op.tBt = make_tmap_bf16(X, a_rows, groups * 64, ldx, 32);
   op.tB = make_tmap_bf16(Wt, (uint64_t)groups * taps * 64, 64, 64, 64);
   return op;
 }
@@ -240,7 +242,10 @@ static inline void run_gemm(vv_engine* e, const GemmOp& op, const GemmEpi& epi) 
     fprintf(stderr, "vvb200: GEMM planned for the CTA-pair kernel has an unsupported epilogue/shape\n");
     abort();
   }
-  launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st, op.bn == 512 ? &op.tBt : nullptr);
+  if (op.s.conv_taps > 0 && conv_pos_supported(op.s, epi))
+    launch_conv_pos(op.tA, op.tBt, op.tB, op.s, epi, e->num_sms, e->st);
+  else
+    launch_gemm(op.tA, op.tB, op.s, epi, op.bn, e->num_sms, e->st, op.bn == 512 ? &op.tBt : nullptr);
   e->launches++;
 }
 

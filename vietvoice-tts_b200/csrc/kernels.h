@@ -77,6 +77,12 @@ void plan_pair_tail(int total_tiles, int clusters, int* full_tiles, int* split);
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
                  int num_sms, cudaStream_t st, const CUtensorMap* tmBt = nullptr);
 
+// conv_pos_embed with the activations resident in shared memory (conv.cu).  tmA128 / tmA32: the activation matrix
+// [rows, groups*64] with 128-row and 32-row boxes; tmB: weights [groups*taps*64, 64] with 64-row boxes.
+bool conv_pos_supported(const GemmShape& s, const GemmEpi& e);
+void launch_conv_pos(const CUtensorMap& tmA128, const CUtensorMap& tmA32, const CUtensorMap& tmB, const GemmShape& s,
+                     const GemmEpi& e, int num_sms, cudaStream_t st);
+
 // Non-causal attention over packed rows. qkv [rows, 3*dim] bf16 (q | k | v, heads of 64), out [rows, dim] bf16.
 // Sequence s covers rows [seq_off[s], seq_off[s]+seq_len[s]). q-tile list: tile_seq[i], tile_q0[i] (row within seq).
 struct AttnParams {
