@@ -103,7 +103,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int kv_len = p.seq_len[seq];
   const int n_kv = (kv_len + 127) >> 7;
 
-  if (threadIdx.x == 0) {
+  // The TMA thread initialises the barriers itself and issues Q and the first K/V stages at once: their L2/HBM
+  // latency then runs under the TMEM allocation and the CTA-wide barrier instead of after them.
+  constexpr int PRE = K_STAGES < V_STAGES ? K_STAGES : V_STAGES;
+  const int n_pre = n_kv < PRE ? n_kv : PRE;
+  if (warp == 4 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < K_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
@@ -119,32 +123,43 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_init(pv_done, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
+    pdl_wait();                  // qkv is the predecessor's output
+    tma_prefetch_desc(&tmQKV);
+    mbar_expect_tx(q_full, TILE_BYTES);
+    tma_load_2d(smem + Q_OFF, &tmQKV, head * 64, seq_row0 + q0, q_full);
+    for (int j = 0; j < n_pre; ++j) {      // ring slots are empty: no wait
+      mbar_expect_tx(&k_full[j], TILE_BYTES);
+      tma_load_2d(smem + K_OFF + j * TILE_BYTES, &tmQKV, p.dim + head * 64, seq_row0 + j * 128, &k_full[j]);
+      mbar_expect_tx(&v_full[j], TILE_BYTES);
+      tma_load_2d(smem + V_OFF + j * TILE_BYTES, &tmQKV, 2 * p.dim + head * 64, seq_row0 + j * 128, &v_full[j]);
+    }
   }
-  if (warp == 4) tmem_alloc(tmem_slot, TM_COLS);
+  if (warp == 5) tmem_alloc(tmem_slot, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                    // prologue done; qkv is the predecessor's output
+  pdl_wait();
 
   if (warp >= 4) {
     setmaxnreg_dec<48>();       // 128 x 208 + 128 x 48 = 256 x 128 registers: two such CTAs fill the SM's register file
     if (warp == 4) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
-        tma_prefetch_desc(&tmQKV);
-        mbar_expect_tx(q_full, TILE_BYTES);
-        tma_load_2d(smem + Q_OFF, &tmQKV, head * 64, seq_row0 + q0, q_full);
         int ks = 0, vs = 0;
         uint32_t kph = 0, vph = 0;
         for (int j = 0; j < n_kv; ++j) {
-          mbar_wait(&k_empty[ks], kph ^ 1);
-          mbar_expect_tx(&k_full[ks], TILE_BYTES);
-          tma_load_2d(smem + K_OFF + ks * TILE_BYTES, &tmQKV, p.dim + head * 64, seq_row0 + j * 128, &k_full[ks]);
+          if (j >= n_pre) {                    // the first n_pre stages were issued before the CTA barrier
+            mbar_wait(&k_empty[ks], kph ^ 1);
+            mbar_expect_tx(&k_full[ks], TILE_BYTES);
+            tma_load_2d(smem + K_OFF + ks * TILE_BYTES, &tmQKV, p.dim + head * 64, seq_row0 + j * 128, &k_full[ks]);
+          }
           if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
-          mbar_wait(&v_empty[vs], vph ^ 1);
-          mbar_expect_tx(&v_full[vs], TILE_BYTES);
-          tma_load_2d(smem + V_OFF + vs * TILE_BYTES, &tmQKV, 2 * p.dim + head * 64, seq_row0 + j * 128, &v_full[vs]);
+          if (j >= n_pre) {
+            mbar_wait(&v_empty[vs], vph ^ 1);
+            mbar_expect_tx(&v_full[vs], TILE_BYTES);
+            tma_load_2d(smem + V_OFF + vs * TILE_BYTES, &tmQKV, 2 * p.dim + head * 64, seq_row0 + j * 128, &v_full[vs]);
+          }
           if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
         }
       }
@@ -341,7 +356,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, TM_COLS);
+  if (warp == 5) tmem_dealloc(tmem_base, TM_COLS);
 }
 
 void launch_attention_impl(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
