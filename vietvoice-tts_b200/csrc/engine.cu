@@ -110,6 +110,7 @@ struct vv_engine {
   // every public entry point that submits work or touches engine state takes this: callers may share one engine
   // between threads (the REST layer of the reference runs requests on worker threads, api/tts_engine.py:79-87)
   std::recursive_mutex mu;
+  std::vector<std::pair<size_t, void*>> pinned_free;   // recycled pinned staging buffers (bytes, pointer)
 };
 
 struct vv_batch {
@@ -129,6 +130,7 @@ struct vv_batch {
   int n_tiles = 0;
   int32_t* ids_d = nullptr;
   int32_t* ids_h = nullptr;             // pinned staging for the id upload
+  size_t ids_h_bytes = 0;
   float* noise0 = nullptr;              // y0 as preprocessed (restored by vv_run_resident)
   std::vector<int64_t> n_samples;
   std::vector<int> dec_ref_len;         // ref_len snapshot the cached decode layout was built for
@@ -172,6 +174,20 @@ static int dev_alloc(std::vector<void*>& list, T** out, size_t count, bool zero 
   if (zero) CK(cudaMemset(p, 0, bytes));
   list.push_back(p);
   *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+// Batch buffers come from the device's stream-ordered memory pool (its release threshold is raised at engine creation
+// so that freed blocks stay cached): a request stream builds and drops a ~1 GB batch for nearly every micro-batch, and
+// cudaMalloc / cudaFree of that (a device-wide synchronisation each) cost 0.1-2 s per new shape — more than the
+// synthesis itself.
+template <typename T>
+static int pool_alloc(std::vector<void*>& list, T** out, size_t count, cudaStream_t st) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  CK(cudaMallocAsync(&p, bytes, st));
+  list.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  CK(cudaMemsetAsync(p, 0, bytes, st));
   return 0;
 }
 #define ENG_LOCK(e) std::lock_guard<std::recursive_mutex> _eng_lock((e)->mu)
@@ -323,6 +339,14 @@ extern "C" int vv_engine_create(const vv_arch* arch, int device, void* stream, v
   e->a = *arch;
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
+  {  // keep freed batch memory cached in the stream-ordered pool instead of returning it to the driver at every sync
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   if (stream) {
     e->st = reinterpret_cast<cudaStream_t>(stream);
   } else {
@@ -557,6 +581,7 @@ extern "C" void vv_engine_destroy(vv_engine* e) {
   cudaStreamSynchronize(e->st);
   for (auto& kv : e->batch_cache) vv_batch_destroy(kv.second);
   for (void* p : e->allocs) cudaFree(p);
+  for (auto& pf : e->pinned_free) cudaFreeHost(pf.second);
   if (e->own_stream) cudaStreamDestroy(e->st);
   delete e;
 }
@@ -618,13 +643,13 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   auto& AL = b->allocs;
 #define UP(dst, vec)                                                                              \
   do {                                                                                            \
-    int _r = dev_alloc(AL, &dst, vec.size());                                                     \
+    int _r = pool_alloc(AL, &dst, vec.size(), e->st);                                             \
     if (_r) { vv_batch_destroy(b); return _r; }                                                   \
-    cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);             \
+    cudaMemcpyAsync(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, e->st); \
   } while (0)
 #define AB(ptr, count)                                                                            \
   do {                                                                                            \
-    int _r = dev_alloc(AL, &ptr, (size_t)(count));                                                \
+    int _r = pool_alloc(AL, &ptr, (size_t)(count), e->st);                                        \
     if (_r) { vv_batch_destroy(b); return _r; }                                                   \
   } while (0)
   UP(b->seq_off_d, b->seq_off);
@@ -637,9 +662,23 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   UP(b->tile_q0_d, tile_q0);
   AB(b->ids_d, M);
   AB(b->noise0, (size_t)R * a.n_mel);
-  if (cudaMallocHost(&b->ids_h, (size_t)R * 4) != cudaSuccess) {
-    vv_batch_destroy(b);
-    return fail(VV_ERR_CUDA, "cudaMallocHost failed");
+  {  // pinned staging buffer for the text ids: recycled through the engine (cudaMallocHost costs milliseconds)
+    const size_t need = (size_t)R * 4;
+    auto best = e->pinned_free.end();
+    for (auto it = e->pinned_free.begin(); it != e->pinned_free.end(); ++it)
+      if (it->first >= need && (best == e->pinned_free.end() || it->first < best->first)) best = it;
+    if (best != e->pinned_free.end()) {
+      b->ids_h = reinterpret_cast<int32_t*>(best->second);
+      b->ids_h_bytes = best->first;
+      e->pinned_free.erase(best);
+    } else {
+      const size_t bytes = std::max<size_t>(need * 2, 1 << 16);      // head room: the next shape is rarely smaller
+      if (cudaMallocHost(&b->ids_h, bytes) != cudaSuccess) {
+        vv_batch_destroy(b);
+        return fail(VV_ERR_CUDA, "cudaMallocHost failed");
+      }
+      b->ids_h_bytes = bytes;
+    }
   }
   b->n_samples.assign(B, 0);
   AB(b->noise, (size_t)R * a.n_mel);
@@ -716,10 +755,10 @@ extern "C" void vv_batch_destroy(vv_batch* b) {
   cudaSetDevice(b->e->device);
   cudaStreamSynchronize(b->e->st);
   for (auto& g : b->graphs) cudaGraphExecDestroy(g.second);
-  for (void* p : b->allocs) cudaFree(p);
+  for (void* p : b->allocs) cudaFreeAsync(p, b->e->st);     // back to the pool, no device-wide synchronisation
   for (int16_t* p : b->audio_d)
-    if (p) cudaFree(p);
-  if (b->ids_h) cudaFreeHost(b->ids_h);
+    if (p) cudaFreeAsync(p, b->e->st);
+  if (b->ids_h) b->e->pinned_free.emplace_back(b->ids_h_bytes, b->ids_h);   // pinned staging buffers are recycled
   delete b;
 }
 
@@ -759,9 +798,9 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
   b->n_samples[idx] = n_samples;
   if (ref_len_out) *ref_len_out = ref_len;
   if (b->audio_cap[idx] < n_samples) {
-    if (b->audio_d[idx]) CK(cudaFree(b->audio_d[idx]));
+    if (b->audio_d[idx]) CK(cudaFreeAsync(b->audio_d[idx], e->st));
     b->audio_d[idx] = nullptr;
-    CK(cudaMalloc(&b->audio_d[idx], (size_t)n_samples * 2));
+    CK(cudaMallocAsync(&b->audio_d[idx], (size_t)n_samples * 2, e->st));
     b->audio_cap[idx] = n_samples;
   }
   CK(cudaMemcpyAsync(b->audio_d[idx], audio, (size_t)n_samples * 2, cudaMemcpyHostToDevice, e->st));
