@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -111,6 +112,15 @@ struct vv_engine {
   // between threads (the REST layer of the reference runs requests on worker threads, api/tts_engine.py:79-87)
   std::recursive_mutex mu;
   std::vector<std::pair<size_t, void*>> pinned_free;   // recycled pinned staging buffers (bytes, pointer)
+  // ONE instantiated graph of the sampling loop per (nfe, launch mode), shared by all batches: a batch keeps only its
+  // captured cudaGraph_t, and running a batch other than the one the executable was last set up for is a
+  // cudaGraphExecUpdate (same topology, new pointers / grids: a few ms) instead of an instantiation (10-140 ms) plus
+  // the first-launch upload.  `owner` is the batch the executable currently holds the parameters of.
+  struct LoopExec {
+    cudaGraphExec_t exec = nullptr;
+    const vv_batch* owner = nullptr;
+  };
+  std::map<std::pair<int, int>, LoopExec> loop_exec;
 };
 
 struct vv_batch {
@@ -161,7 +171,7 @@ struct vv_batch {
   std::vector<GemmOp> op_qkv, op_out, op_ff1, op_ff2, op_tpw1, op_tpw2, op_vpw1, op_vpw2;
   GemmOp op_vemb, op_vhead;
   CUtensorMap tQKV;
-  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, cudaGraph_t> graphs;       // captured sampling loop per nfe (the executable lives in the engine)
   std::map<int, int64_t> graph_launches;
 };
 
@@ -582,6 +592,8 @@ extern "C" void vv_engine_destroy(vv_engine* e) {
   for (auto& kv : e->batch_cache) vv_batch_destroy(kv.second);
   for (void* p : e->allocs) cudaFree(p);
   for (auto& pf : e->pinned_free) cudaFreeHost(pf.second);
+  for (auto& le : e->loop_exec)
+    if (le.second.exec) cudaGraphExecDestroy(le.second.exec);
   if (e->own_stream) cudaStreamDestroy(e->st);
   delete e;
 }
@@ -754,7 +766,9 @@ extern "C" void vv_batch_destroy(vv_batch* b) {
   if (!b) return;
   cudaSetDevice(b->e->device);
   cudaStreamSynchronize(b->e->st);
-  for (auto& g : b->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : b->graphs) cudaGraphDestroy(g.second);
+  for (auto& le : b->e->loop_exec)
+    if (le.second.owner == b) le.second.owner = nullptr;     // the executable must be updated before its next launch
   for (void* p : b->allocs) cudaFreeAsync(p, b->e->st);     // back to the pool, no device-wide synchronisation
   for (int16_t* p : b->audio_d)
     if (p) cudaFreeAsync(p, b->e->st);
@@ -970,21 +984,40 @@ extern "C" int vv_sample(vv_batch* b, int nfe, int first_step, int n_steps) {
     if (it == b->graphs.end()) {
       cudaGraph_t g = nullptr;
       const int64_t before = e->launches;
+      const auto tc0 = std::chrono::steady_clock::now();
       CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
       int rc = 0;
       for (int s = 0; s < n_steps && rc == 0; ++s) rc = run_step(b, *mt, s, -1);
       cudaError_t ce = cudaStreamEndCapture(e->st, &g);
+      if (getenv("VVB200_VERBOSE"))
+        fprintf(stderr, "vvb200: capture %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
       if (rc) return rc;
       if (ce != cudaSuccess) return fail(VV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-      cudaGraphExec_t ge = nullptr;
-      CK(cudaGraphInstantiate(&ge, g, 0));
-      cudaGraphDestroy(g);
       b->graph_launches[nfe] = e->launches - before;
       e->launches = before;
-      b->graphs[nfe] = ge;
+      b->graphs[nfe] = g;
       it = b->graphs.find(nfe);
     }
-    CK(cudaGraphLaunch(it->second, e->st));
+    const auto tg0 = std::chrono::steady_clock::now();
+    vv_engine::LoopExec& le = e->loop_exec[std::make_pair(nfe, want_pdl(b) ? 1 : 0)];
+    const bool verbose_g = getenv("VVB200_VERBOSE") && le.owner != b;
+    if (le.exec && le.owner != b) {
+      cudaGraphExecUpdateResultInfo info;
+      if (cudaGraphExecUpdate(le.exec, it->second, &info) != cudaSuccess) {   // different topology (tile plan): rebuild
+        (void)cudaGetLastError();
+        cudaGraphExecDestroy(le.exec);
+        le.exec = nullptr;
+      }
+    }
+    if (!le.exec) CK(cudaGraphInstantiate(&le.exec, it->second, 0));
+    le.owner = b;
+    const auto tg1 = std::chrono::steady_clock::now();
+    CK(cudaGraphLaunch(le.exec, e->st));
+    if (verbose_g)
+      fprintf(stderr, "vvb200: graph exec update/instantiate %.1f ms, launch call %.1f ms\n",
+              std::chrono::duration<double, std::milli>(tg1 - tg0).count(),
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg1).count());
     e->launches += b->graph_launches[nfe];
   } else {
     for (int s = first_step; s < first_step + n_steps; ++s) TRY(run_step(b, *mt, s, -1));
@@ -1417,7 +1450,11 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
       return true;
     };
     while (e->batch_cache.size() >= cap && evict_lru()) {}
+    const auto tb0 = std::chrono::steady_clock::now();
     int rc = vv_batch_create(e, B, key.data(), &b);
+    if (getenv("VVB200_VERBOSE"))
+      fprintf(stderr, "vvb200: batch create %.1f ms\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
     while (rc == VV_ERR_CUDA && evict_lru()) {     // out of device memory: drop cached batches until it fits
       (void)cudaGetLastError();
       rc = vv_batch_create(e, B, key.data(), &b);
