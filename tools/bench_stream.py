@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--rate", type=float, default=12.0, help="mean arrivals per second (Poisson), whole job")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-batch-chunks", type=int, default=8)
+    ap.add_argument("--max-batch-frames", type=int, default=8 * 1800)
     args = ap.parse_args()
 
     import torch
@@ -75,7 +76,8 @@ def main():
             for nfe in (16, 32, 64):
                 sch.submit(SENTENCES[0], nfe=nfe).result(timeout=600)
         lat, audio_s, errs = [], [], []
-        with RequestScheduler(tts, max_batch_chunks=args.max_batch_chunks, rank=rank, world=world) as sch:
+        with RequestScheduler(tts, max_batch_chunks=args.max_batch_chunks, max_batch_frames=args.max_batch_frames,
+                              rank=rank, world=world) as sch:
             lock = threading.Lock()
             t_start = time.time()
 
@@ -123,7 +125,7 @@ def main():
             "latency_p95_ms": 1e3 * lat[min(len(lat) - 1, int(0.95 * len(lat)))] if lat else None,
             "micro_batches": stats[3], "chunks": stats[4],
             "config": {"workload": "configs[4]: Poisson request stream, 6 voices, NFE 16/32/64 (p 0.25/0.5/0.25), 1-3 "
-                                   "sentences per request", "max_batch_chunks": args.max_batch_chunks,
+                                   "sentences per request", "max_batch_chunks": args.max_batch_chunks, "max_batch_frames": args.max_batch_frames,
                        "weights": "random-init F5-TTS-Base/Vocos shapes, seed 9527"},
         }
         print(json.dumps(line))
