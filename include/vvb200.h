@@ -118,6 +118,10 @@ typedef struct vv_request {
   int64_t pcm_capacity;
   int64_t n_out;            /* written by the call                                      */
 } vv_request;
+/* Synchronous: returns when every pcm_out is filled.  Thread-safe on one engine (calls are serialised by the engine's
+ * own lock, like every other entry point; vv_last_error is per thread).  Batches are cached per tuple of total_frames
+ * in an LRU of VVB200_BATCH_CACHE entries (default 6); their buffers come from the device's stream-ordered memory
+ * pool and all batches share one instantiated CUDA graph of the sampling loop per nfe, updated in place. */
 int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed);
 
 /* Same path with every input already resident in HBM (uploaded by a previous vv_preprocess of each chunk): recomputes
