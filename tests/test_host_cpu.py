@@ -183,3 +183,65 @@ def test_model_config_contract(tmp_path):
             ModelConfig(model_cache_dir=str(tmp_path), **bad)
     with pytest.raises(RuntimeError):          # no network, no cached file -> "Model validation failed"
         ModelConfig(model_cache_dir=str(tmp_path / "empty"), model_url="http://127.0.0.1:9/none")
+
+
+def test_select_sample_rules_and_messages(tmp_path):
+    """Voice selection of the session manager (/root/reference/vietvoicetts/core/model.py:137-214): config defaults
+    are merged before filtering, enum validation and its messages, the custom-prompt early-out, the silent fallback
+    to voice 0, `sample_iteration`, and the prompt bytes read from `cleaned_audios/` of the tar (cached here)."""
+    import tarfile
+    from vietvoice_tts_b200 import artifact
+    from vietvoice_tts_b200.arch import TINY
+    from vietvoice_tts_b200.host.model import ModelSessionManager
+    from vietvoice_tts_b200.host.model_config import ModelConfig, MODEL_GENDER
+
+    voices = [{"gender": "female", "group": "audiobook", "area": "northern", "emotion": "neutral"},
+              {"gender": "male", "group": "news", "area": "southern", "emotion": "serious"},
+              {"gender": "male", "group": "news", "area": "southern", "emotion": "serious"}]
+    artifact.build_model_tar(str(tmp_path / "model-bin.pt"), TINY, seed=1, voices=voices, prompt_seconds=0.2)
+    cfg = ModelConfig(model_cache_dir=str(tmp_path), gender=None, group=None, area=None, emotion=None)
+    m = ModelSessionManager(cfg)
+    assert m.providers[-1] == "CPUExecutionProvider"
+    with tarfile.open(cfg.model_path) as tar:
+        m.sample_metadata = json.load(tar.extractfile("audio_metadata.json"))
+        wav = [tar.extractfile("cleaned_audios/" + s["file_name"]).read() for s in m.sample_metadata]
+
+    audio, text = m.select_sample()                                   # no filter at all: first voice
+    assert audio == wav[0] and text == m.sample_metadata[0]["text"]
+    audio, _ = m.select_sample(gender="male")
+    assert audio == wav[1]
+    audio, _ = m.select_sample(gender="male", sample_iteration=1)
+    assert audio == wav[2]
+    with pytest.raises(ValueError, match="sample_iteration 2 is out of range. Only 2 samples available"):
+        m.select_sample(gender="male", sample_iteration=2)
+    audio, _ = m.select_sample(emotion="happy")                       # nothing matches: silent fallback to voice 0
+    assert audio == wav[0]
+    with pytest.raises(ValueError, match=r"Invalid gender: robot. Must be one of \['male', 'female'\]"):
+        m.select_sample(gender="robot")
+    with pytest.raises(ValueError, match="Invalid area"):
+        m.select_sample(area="western")
+    assert MODEL_GENDER == ["male", "female"]
+
+    # custom prompt: text required, file must exist, no voice options may be active
+    prompt = tmp_path / "p.wav"
+    prompt.write_bytes(wav[0])
+    with pytest.raises(ValueError, match="Reference text is required"):
+        m.select_sample(reference_audio=str(prompt))
+    with pytest.raises(FileNotFoundError, match="Reference audio file not found"):
+        m.select_sample(reference_audio=str(tmp_path / "nope.wav"), reference_text="x")
+    with pytest.raises(ValueError, match=r"Cannot use reference audio and text with options: \['gender'\]"):
+        m.select_sample(gender="male", reference_audio=str(prompt), reference_text="x")
+    assert m.select_sample(reference_audio=str(prompt), reference_text="xin chào") == (str(prompt), "xin chào")
+
+    # config defaults count as options (SURVEY Appendix B): a custom prompt with the stock config raises
+    m2 = ModelSessionManager(ModelConfig(model_cache_dir=str(tmp_path)))
+    m2.sample_metadata = m.sample_metadata
+    with pytest.raises(ValueError, match="Cannot use reference audio and text with options"):
+        m2.select_sample(reference_audio=str(prompt), reference_text="x")
+    audio, _ = m2.select_sample()                                     # female / audiobook / northern / neutral
+    assert audio == wav[0]
+
+    # a metadata row without the filtered key -> the reference's KeyError wrapper
+    m.sample_metadata = [{"file_name": "voice_000.wav", "text": "t"}]
+    with pytest.raises(ValueError, match="Sample not found for gender: male"):
+        m.select_sample(gender="male")

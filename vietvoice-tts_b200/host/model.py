@@ -2,10 +2,10 @@
 
 Mirror of the reference interface `ModelSessionManager` (/root/reference/vietvoicetts/core/model.py:18-224): same
 attributes (`sessions`, `input_names`, `output_names`, `sample_metadata`, `vocab_path`, `providers`), same tar member
-names, same voice-selection rules and error types.  Sessions are created through `vietvoice_tts_b200.ort_shim`
-(libvvb200.so) instead of onnxruntime.  Additions that do not change results: the tar index and the prompt bytes are
-cached (the reference re-opens the tar on every call, model.py:204-211 — SURVEY 8f rank 1), and `engine` exposes
-the shared B200 engine for the batched fast path.
+names, same voice-selection rules, error types and messages (callers match on them).  Sessions are created through
+`vietvoice_tts_b200.ort_shim` (libvvb200.so) instead of onnxruntime.  Additions that do not change results: the prompt
+bytes are cached per file name (the reference re-opens the tar on every call, model.py:204-211 — SURVEY 8f rank 1),
+and `engine` exposes the shared B200 engine for the batched fast path.
 """
 from __future__ import annotations
 
@@ -22,8 +22,25 @@ from loguru import logger
 from .. import ort_shim as onnxruntime
 from .model_config import MODEL_AREA, MODEL_EMOTION, MODEL_GENDER, MODEL_GROUP, ModelConfig
 
-_GRAPH_FILES = {"preprocess": "preprocess.onnx", "transformer": "transformer.onnx", "decode": "decode.onnx"}
-_FILTER_DOMAINS = (("gender", MODEL_GENDER), ("group", MODEL_GROUP), ("area", MODEL_AREA), ("emotion", MODEL_EMOTION))
+# graph key -> archive member suffix (model.py:73-77)
+_GRAPH_FILES = (("preprocess", "preprocess.onnx"), ("transformer", "transformer.onnx"), ("decode", "decode.onnx"))
+# voice attribute -> values the metadata table uses (model.py:151-167)
+_VOICE_DOMAINS = (("gender", MODEL_GENDER), ("group", MODEL_GROUP), ("area", MODEL_AREA), ("emotion", MODEL_EMOTION))
+# numeric / boolean session options copied verbatim from the config (model.py:52-57)
+_COPIED_OPTIONS = ("log_severity_level", "log_verbosity_level", "inter_op_num_threads", "intra_op_num_threads",
+                   "enable_cpu_mem_arena")
+_SPIN_ENTRIES = ("session.intra_op.allow_spinning", "session.inter_op.allow_spinning", "session.set_denormal_as_zero")
+
+
+def _member_bytes(tar: tarfile.TarFile, names: List[str], suffix: str, missing: str, unreadable: str) -> bytes:
+    """Bytes of the first archive member whose name ends with `suffix`."""
+    hit = [n for n in names if n.endswith(suffix)]
+    if not hit:
+        raise FileNotFoundError(missing)
+    handle = tar.extractfile(hit[0])
+    if not handle:
+        raise RuntimeError(unreadable)
+    return handle.read()
 
 
 class ModelSessionManager:
@@ -40,92 +57,102 @@ class ModelSessionManager:
         self.vocab_path: Optional[str] = None
         self._prompt_cache: Dict[str, bytes] = {}
 
+    # ------------------------------------------------------------------------------------------ sessions
     def _get_optimal_providers(self) -> List[str]:
-        available = onnxruntime.get_available_providers()
-        chosen = [p for p in ("CUDAExecutionProvider", "CPUExecutionProvider") if p in available]
-        if "CPUExecutionProvider" not in chosen:
-            chosen.append("CPUExecutionProvider")
-        return chosen
+        have = set(onnxruntime.get_available_providers())
+        order = ["CUDAExecutionProvider"] if "CUDAExecutionProvider" in have else []
+        return order + ["CPUExecutionProvider"]
 
     def _create_session_options(self) -> onnxruntime.SessionOptions:
-        opts = onnxruntime.SessionOptions()
-        opts.log_severity_level = self.config.log_severity_level
-        opts.log_verbosity_level = self.config.log_verbosity_level
-        opts.inter_op_num_threads = self.config.inter_op_num_threads
-        opts.intra_op_num_threads = self.config.intra_op_num_threads
-        opts.enable_cpu_mem_arena = self.config.enable_cpu_mem_arena
-        opts.execution_mode = onnxruntime.ExecutionMode.ORT_SEQUENTIAL
-        opts.graph_optimization_level = onnxruntime.GraphOptimizationLevel.ORT_ENABLE_ALL
-        for key in ("session.intra_op.allow_spinning", "session.inter_op.allow_spinning", "session.set_denormal_as_zero"):
-            opts.add_session_config_entry(key, "1")
-        opts.add_session_config_entry("vvb200.fuse_nfe", str(self.config.fuse_nfe))
-        return opts
+        so = onnxruntime.SessionOptions()
+        for attr in _COPIED_OPTIONS:
+            setattr(so, attr, getattr(self.config, attr))
+        so.execution_mode = onnxruntime.ExecutionMode.ORT_SEQUENTIAL
+        so.graph_optimization_level = onnxruntime.GraphOptimizationLevel.ORT_ENABLE_ALL
+        for entry in _SPIN_ENTRIES:
+            so.add_session_config_entry(entry, "1")
+        so.add_session_config_entry("vvb200.fuse_nfe", str(self.config.fuse_nfe))
+        return so
+
+    def _bind_session(self, graph: str, blob: bytes) -> None:
+        sess = onnxruntime.InferenceSession(blob, sess_options=self._create_session_options(), providers=self.providers)
+        self.sessions[graph] = sess
+        self.input_names[graph] = [node.name for node in sess.get_inputs()]        # order is the ABI
+        self.output_names[graph] = [node.name for node in sess.get_outputs()]
+
+    def _drop_temp_dir(self) -> None:
+        if self.temp_dir and Path(self.temp_dir).exists():
+            shutil.rmtree(self.temp_dir)
+        self.temp_dir = None
 
     def _load_models_from_file(self) -> None:
-        model_path = self.config.ensure_model_downloaded()
-        if not Path(model_path).exists():
-            raise FileNotFoundError(f"Model file not found: {model_path}")
+        archive = self.config.ensure_model_downloaded()
+        if not Path(archive).exists():
+            raise FileNotFoundError(f"Model file not found: {archive}")
         try:
-            with tarfile.open(model_path, "r") as tar:
+            with tarfile.open(archive, "r") as tar:
                 names = tar.getnames()
                 self.sample_metadata = json.load(tar.extractfile("audio_metadata.json"))
-                for graph, fname in _GRAPH_FILES.items():
-                    member = next((m for m in names if m.endswith(fname)), None)
-                    if not member:
-                        raise FileNotFoundError(f"Model file '{fname}' not found in model archive")
-                    fh = tar.extractfile(member)
-                    if not fh:
-                        raise RuntimeError(f"Failed to extract {fname} from model archive")
-                    session = onnxruntime.InferenceSession(fh.read(), sess_options=self._create_session_options(),
-                                                           providers=self.providers)
-                    self.sessions[graph] = session
-                    self.input_names[graph] = [i.name for i in session.get_inputs()]
-                    self.output_names[graph] = [o.name for o in session.get_outputs()]
-                vocab_member = next((m for m in names if m.endswith("vocab.txt")), None)
-                if not vocab_member:
-                    raise FileNotFoundError("Vocabulary file 'vocab.txt' not found in model archive")
-                fh = tar.extractfile(vocab_member)
-                if not fh:
-                    raise RuntimeError("Failed to extract vocab.txt from model archive")
-                self.temp_dir = tempfile.mkdtemp(prefix="tts_vocab_")
-                vocab_file = Path(self.temp_dir) / "vocab.txt"
-                vocab_file.write_bytes(fh.read())
-                self.vocab_path = str(vocab_file)
+                for graph, fname in _GRAPH_FILES:
+                    self._bind_session(graph, _member_bytes(
+                        tar, names, fname, f"Model file '{fname}' not found in model archive",
+                        f"Failed to extract {fname} from model archive"))
+                vocab = _member_bytes(tar, names, "vocab.txt", "Vocabulary file 'vocab.txt' not found in model archive",
+                                      "Failed to extract vocab.txt from model archive")
+            self.temp_dir = tempfile.mkdtemp(prefix="tts_vocab_")
+            target = Path(self.temp_dir, "vocab.txt")
+            target.write_bytes(vocab)
+            self.vocab_path = str(target)
         except Exception as exc:
-            if self.temp_dir and Path(self.temp_dir).exists():
-                shutil.rmtree(self.temp_dir)
-                self.temp_dir = None
+            self._drop_temp_dir()
             raise RuntimeError(f"Failed to load models from file: {str(exc)}")
 
     def load_models(self) -> None:
-        onnxruntime.set_seed(self.config.random_seed)
-        random.seed(self.config.random_seed)
+        seed = self.config.random_seed
+        onnxruntime.set_seed(seed)
+        random.seed(seed)
         self._load_models_from_file()
 
     @property
     def engine(self):
         """The B200 engine shared by the three sessions (batched fast path)."""
-        sh = self.sessions["transformer"]._sh
-        sh.ensure_final()
-        return sh.engine
+        shared = self.sessions["transformer"]._sh
+        shared.ensure_final()
+        return shared.engine
 
-    def select_sample(self, gender: Optional[str] = None, group: Optional[str] = None, area: Optional[str] = None,
-                      emotion: Optional[str] = None, sample_iteration: Optional[int] = None,
-                      reference_audio: Optional[str] = None, reference_text: Optional[str] = None) -> Tuple[str, str]:
-        """-> (prompt wav bytes | path, prompt text).  Config defaults are merged BEFORE filtering, so a custom
-        prompt combined with non-None defaults raises, exactly as upstream."""
-        requested = {"gender": gender or self.config.gender, "group": group or self.config.group,
-                     "area": area or self.config.area, "emotion": emotion or self.config.emotion}
-        filters = {}
-        for key, domain in _FILTER_DOMAINS:
-            value = requested[key]
+    # ------------------------------------------------------------------------------------------ voices
+    def _voice_filters(self, asked: Dict[str, Optional[str]]) -> Dict[str, str]:
+        """Config defaults are merged BEFORE validation and filtering."""
+        out: Dict[str, str] = {}
+        for key, domain in _VOICE_DOMAINS:
+            value = asked[key] or getattr(self.config, key)
             if value is None:
                 continue
             if value not in domain:
                 raise ValueError(f"Invalid {key}: {value}. Must be one of {domain}")
-            filters[key] = value
+            out[key] = value
+        return out
 
-        if reference_audio is not None:
+    def _prompt_bytes(self, file_name: str) -> bytes:
+        cached = self._prompt_cache.get(file_name)
+        if cached is not None:
+            return cached
+        with tarfile.open(self.config.ensure_model_downloaded(), "r") as tar:
+            handle = tar.extractfile("cleaned_audios/" + file_name)
+            if not handle:
+                raise FileNotFoundError(f"Audio file {file_name} not found in model archive")
+            data = handle.read()
+        self._prompt_cache[file_name] = data
+        return data
+
+    def select_sample(self, gender: Optional[str] = None, group: Optional[str] = None, area: Optional[str] = None,
+                      emotion: Optional[str] = None, sample_iteration: Optional[int] = None,
+                      reference_audio: Optional[str] = None, reference_text: Optional[str] = None) -> Tuple[str, str]:
+        """-> (prompt wav bytes | path, prompt text).  A custom prompt combined with non-None config defaults raises,
+        exactly as upstream."""
+        filters = self._voice_filters({"gender": gender, "group": group, "area": area, "emotion": emotion})
+
+        if reference_audio is not None:                     # custom prompt: early out (model.py:169-177)
             if reference_text is None:
                 raise ValueError("Reference text is required when using reference audio")
             if not Path(reference_audio).exists():
@@ -136,37 +163,30 @@ class ModelSessionManager:
             return reference_audio, reference_text
 
         try:
-            matches = [(s, i) for i, s in enumerate(self.sample_metadata)
-                       if all(s[k] == v for k, v in filters.items())]
-            if not matches:
-                sample, idx = self.sample_metadata[0], 0          # silent fallback, as upstream
-            elif sample_iteration is not None:
-                if sample_iteration >= len(matches):
-                    raise ValueError(f"sample_iteration {sample_iteration} is out of range. Only {len(matches)} "
-                                     f"samples available for the given filters.")
-                sample, idx = matches[sample_iteration]
+            rows = list(enumerate(self.sample_metadata))
+            hits = [(i, row) for i, row in rows if all(row[k] == v for k, v in filters.items())]
+            if not hits:
+                pick = 0                                    # silent fallback to the first voice, as upstream
+            elif sample_iteration is None:
+                pick = hits[0][0]
+            elif sample_iteration >= len(hits):
+                raise ValueError(f"sample_iteration {sample_iteration} is out of range. Only {len(hits)} "
+                                 f"samples available for the given filters.")
             else:
-                sample, idx = matches[0]
-            logger.info(f"Selected sample #{idx} with gender: {sample['gender']}, group: {sample['group']}, "
-                        f"area: {sample['area']}, emotion: {sample['emotion']}")
-            fname = sample["file_name"]
-            audio = self._prompt_cache.get(fname)
-            if audio is None:
-                with tarfile.open(self.config.ensure_model_downloaded(), "r") as tar:
-                    fh = tar.extractfile("cleaned_audios/" + fname)
-                    if not fh:
-                        raise FileNotFoundError(f"Audio file {fname} not found in model archive")
-                    audio = fh.read()
-                self._prompt_cache[fname] = audio
-            text = sample["text"]
+                pick = hits[sample_iteration][0]
+            row = self.sample_metadata[pick]
+            logger.info(f"Selected sample #{pick} with gender: {row['gender']}, group: {row['group']}, "
+                        f"area: {row['area']}, emotion: {row['emotion']}")
+            return self._prompt_bytes(row["file_name"]), row["text"]
         except KeyError:
-            raise ValueError(f"Sample not found for gender: {gender}, group: {group}, area: {area}, emotion: {emotion}")
-        return audio, text
+            raise ValueError(f"Sample not found for gender: {gender or self.config.gender}, "
+                             f"group: {group or self.config.group}, area: {area or self.config.area}, "
+                             f"emotion: {emotion or self.config.emotion}")
 
+    # ------------------------------------------------------------------------------------------ lifetime
     def cleanup(self) -> None:
-        if self.temp_dir and Path(self.temp_dir).exists():
-            shutil.rmtree(self.temp_dir)
-            self.temp_dir = None
+        if self.temp_dir:
+            self._drop_temp_dir()
             self.vocab_path = None
 
     def __del__(self):

@@ -21,31 +21,51 @@ MODEL_AREA = ["northern", "southern", "central"]
 MODEL_EMOTION = ["neutral", "serious", "monotone", "sad", "surprised", "happy", "angry"]
 
 
+def _fetch(url: str, target: Path) -> None:
+    """Download `url` to `target`; a partial file never survives a failure (core/model_config.py:83-98)."""
+    logger.info(f"Downloading model from {url}")
+    try:
+        urllib.request.urlretrieve(url, target)
+    except urllib.error.URLError as exc:
+        raise RuntimeError(f"Failed to download model from {url}: {exc}")
+    except Exception as exc:
+        if target.exists():
+            target.unlink()
+        raise RuntimeError(f"Failed to download model: {exc}")
+
+
+def _wav_seconds(path: str) -> float:
+    import wave
+    with wave.open(path, "rb") as w:
+        return w.getnframes() / float(w.getframerate())
+
+
 @dataclass
 class ModelConfig:
-    # model artefact
+    # ---- where the artefact lives (read by ModelSessionManager._load_models_from_file / select_sample)
     model_url: str = "https://huggingface.co/nguyenvulebinh/VietVoice-TTS/resolve/main/model-bin.pt"
     model_cache_dir: str = "models"
     model_filename: str = "model-bin.pt"
-    # sampler
+    # ---- sampler: nfe_step - 1 transformer calls of stride fuse_nfe (tts_engine.py:157); speed scales the duration
+    #      model of _prepare_inputs; random_seed seeds the sessions and keys the engine's Philox y0
     nfe_step: int = 32
     fuse_nfe: int = 1
     sample_rate: int = 24000
     speed: float = 0.9
     random_seed: int = 9527
     hop_length: int = 256
-    # voice selection
+    # ---- default voice: merged into every select_sample call BEFORE filtering (None = no constraint)
     gender: Optional[str] = "female"
     area: Optional[str] = "northern"
     emotion: Optional[str] = "neutral"
     group: Optional[str] = "audiobook"
-    # text
+    # ---- text: used as a REGEX by calculate_text_length, not as a character class (SURVEY 8a, row a11)
     pause_punctuation: str = r".,?!:"
-    # audio
+    # ---- chunking and joining (seconds): cross-fade overlap, chunk budget incl. the prompt, shortest useful target
     cross_fade_duration: float = 0.1
     max_chunk_duration: float = 20.0
     min_target_duration: float = 1.0
-    # executor knobs of the reference (accepted, unused by the B200 engine)
+    # ---- executor knobs of the reference: accepted and forwarded to SessionOptions, without effect on the B200 engine
     log_severity_level: int = 4
     log_verbosity_level: int = 4
     inter_op_num_threads: int = 0
@@ -53,10 +73,10 @@ class ModelConfig:
     enable_cpu_mem_arena: bool = True
 
     def __post_init__(self):
-        if not 0.1 <= self.speed <= 5.0:
-            raise ValueError("Speed must be between 0.1 and 5.0")
-        if not 1 <= self.nfe_step <= 100:
-            raise ValueError("NFE step must be between 1 and 100")
+        for ok, message in ((0.1 <= self.speed <= 5.0, "Speed must be between 0.1 and 5.0"),
+                            (1 <= self.nfe_step <= 100, "NFE step must be between 1 and 100")):
+            if not ok:
+                raise ValueError(message)
         self.validate_paths()
 
     @property
@@ -64,20 +84,13 @@ class ModelConfig:
         return str(Path(self.model_cache_dir).expanduser() / self.model_filename)
 
     def ensure_model_downloaded(self) -> str:
+        """Path of the cached artefact, downloading it first if it is not there."""
         target = Path(self.model_path)
         target.parent.mkdir(parents=True, exist_ok=True)
         if target.exists():
             logger.info(f"Using cached model: {target}")
-            return str(target)
-        logger.info(f"Downloading model from {self.model_url}")
-        try:
-            urllib.request.urlretrieve(self.model_url, target)
-        except urllib.error.URLError as exc:
-            raise RuntimeError(f"Failed to download model from {self.model_url}: {exc}")
-        except Exception as exc:
-            if target.exists():
-                target.unlink()          # never leave a partial download behind
-            raise RuntimeError(f"Failed to download model: {exc}")
+        else:
+            _fetch(self.model_url, target)
         return str(target)
 
     def validate_paths(self):
@@ -87,20 +100,18 @@ class ModelConfig:
             raise RuntimeError(f"Model validation failed: {exc}")
 
     def validate_with_reference_audio(self, reference_audio_path: str) -> bool:
-        """True when prompt + 1 s safety margin + min_target_duration fits in max_chunk_duration."""
+        """True when prompt + 1 s safety margin + min_target_duration fits in max_chunk_duration (PCM WAV prompts;
+        the reference decodes any container through pydub/ffmpeg, absent offline)."""
         try:
-            import wave
-            with wave.open(reference_audio_path, "rb") as w:
-                ref_duration = w.getnframes() / float(w.getframerate())
+            need = _wav_seconds(reference_audio_path) + 1.0 + self.min_target_duration
         except Exception as exc:
             logger.error(f"Error validating reference audio: {exc}")
             return False
-        need = ref_duration + 1.0 + self.min_target_duration
-        if self.max_chunk_duration < need:
-            logger.error(f"Configuration Error: reference audio {ref_duration:.1f}s needs max_chunk_duration > {need:.1f}s "
-                         f"(current {self.max_chunk_duration:.1f}s)")
-            return False
-        return True
+        if self.max_chunk_duration >= need:
+            return True
+        logger.error(f"Configuration Error: the reference audio needs max_chunk_duration > {need:.1f}s "
+                     f"(current {self.max_chunk_duration:.1f}s)")
+        return False
 
     @classmethod
     def from_dict(cls, config_dict: dict) -> "ModelConfig":
