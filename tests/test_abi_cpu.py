@@ -57,3 +57,15 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.split()[0] == "100"
+
+
+def test_makefile_builds_every_cuda_source():
+    """a kernel file that is not in the Makefile's SRCS silently stays out of libvvb200.so"""
+    import glob
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vietvoice-tts_b200", "csrc")
+    with open(os.path.join(csrc, "Makefile")) as f:
+        srcs = re.search(r"^SRCS\s*:=\s*(.*)$", f.read(), re.M).group(1).split()
+    on_disk = sorted(os.path.basename(p) for p in glob.glob(os.path.join(csrc, "*.cu")))
+    assert sorted(srcs) == on_disk
