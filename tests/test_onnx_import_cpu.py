@@ -158,3 +158,17 @@ def test_converted_weights_drive_the_oracle_identically():
         outs.append(list(pre) + [x, S.decode.run(x, pre[7])[0]])
     for a, b in zip(*outs):
         np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_full_architecture_parameter_count():
+    """the blob layout at the named size: 14.69 M parameters per DiT block, 323 M in the 22 blocks"""
+    shapes = oi.expected_shapes(FULL)
+    n = lambda prefix: sum(int(np.prod(s)) for k, s in shapes.items() if k.startswith(prefix))
+    d = FULL.dim
+    assert n("dit.blocks.0.") == 14 * d * d + 13 * d == 14_693_376
+    assert n("dit.blocks.") == 22 * 14_693_376
+    assert shapes["dit.in.w"] == (d, FULL.in_dim) == (1024, 712)
+    assert shapes["dit.pos.c1.w"] == (d, d // FULL.conv_pos_groups, FULL.conv_pos_k) == (1024, 64, 31)
+    assert shapes["pre.text_embed"] == (FULL.vocab + 1, FULL.text_dim)
+    assert shapes["voc.head.w"] == (FULL.n_fft + 2, FULL.voc_dim) == (1026, 512)
+    assert 13_000_000 < n("voc.") < 14_500_000          # Vocos-mel-24k backbone + ISTFT head
