@@ -17,9 +17,9 @@
 //   * tried and dropped: explicit MUFU ping-pong between two tiles in a persistent CTA (a single softmax warp cannot
 //     saturate its scheduler's MUFU, so taking turns only serialises two latency-bound streams), two threads per
 //     query row (the per-tile maximum exchange and the exposed PV round trip cost more than the extra warps gain);
-//   * one score pair in four takes its exp2 on the FMA/ALU pipes (packed degree-3 polynomial, attn_softmax.cuh)
-//     instead of MUFU.EX2: -2..3 % kernel time; two pairs in four is 7 % SLOWER (12 instructions replace 2, and the
-//     loop becomes issue-bound).
+//   * one score pair in EIGHT takes its exp2 on the FMA/ALU pipes (packed degree-3 polynomial, attn_softmax.cuh)
+//     instead of MUFU.EX2.  Sweep, back to back on one box: 0/8 272-277 us, 1/8 265 us, 2/8 270 us, 3/8 284-319 us,
+//     4/8 297 us — 12 instructions replace 2, so the loop turns issue-bound quickly.
 //   S = Q K^T : tcgen05.mma M128 N128 K64 -> TMEM cols [0,128)
 //   P (bf16)  : tcgen05.st -> TMEM cols [128,192); O += P V : tcgen05.mma M128 N64 K128, A from TMEM, V MN-major
 //               straight from the TMA tile; O in TMEM cols [192,256)

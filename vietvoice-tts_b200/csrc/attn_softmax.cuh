@@ -3,6 +3,9 @@
 #include "ptx.cuh"
 
 
+#ifndef VV_ATTN_POLY8
+#define VV_ATTN_POLY8 1     // of every 8 score pairs, this many take exp2 on the FMA pipe (0: use VV_ATTN_POLY of every 4)
+#endif
 #ifndef VV_ATTN_POLY
 #define VV_ATTN_POLY 1      // of every 4 score pairs, this many take the FMA-pipe exp2 instead of MUFU.EX2
 #endif
@@ -63,13 +66,13 @@ __device__ __forceinline__ void softmax_row(const uint32_t (&s)[128], float scal
       ffma2(x2, x3, val(k + 2), val(k + 3), scale_log2, -m);
       // pair slots 0..3 repeat every 8 elements; the LAST VV_ATTN_POLY slots of each group go to the FMA pipe
       float e0, e1, e2, e3;
-      if (((i / 4) % 2) * 2 + 0 >= 4 - VV_ATTN_POLY) {
+      if (VV_ATTN_POLY8 ? (((i / 2) % 8) >= 8 - VV_ATTN_POLY8) : (((i / 4) % 2) * 2 + 0 >= 4 - VV_ATTN_POLY)) {
         poly_exp2_pair(x0, x1, e0, e1);
       } else {
         e0 = fast_exp2(x0);
         e1 = fast_exp2(x1);
       }
-      if (((i / 4) % 2) * 2 + 1 >= 4 - VV_ATTN_POLY) {
+      if (VV_ATTN_POLY8 ? (((i / 2 + 1) % 8) >= 8 - VV_ATTN_POLY8) : (((i / 4) % 2) * 2 + 1 >= 4 - VV_ATTN_POLY)) {
         poly_exp2_pair(x2, x3, e2, e3);
       } else {
         e2 = fast_exp2(x2);
