@@ -13,6 +13,10 @@
  *   vv_decode            <- sessions['decode'].run      (2 feeds -> 1 output)   vietvoicetts/core/tts_engine.py:176-187
  *   vv_synthesize_batch  <- the whole preprocess -> steps -> decode body of the loop at tts_engine.py:225-238,
  *                           for B independent chunks at once, HOST buffers in, HOST int16 PCM out
+ *   vv_prompt_put / vv_prompt_drop / vv_prompt_cache_clear / vv_preprocess_prompt
+ *       <- ModelSessionManager.select_sample re-reading the prompt WAV from the tar on every call
+ *          (vietvoicetts/core/model.py:204-211) and TTSEngine's never-used sample_cache
+ *          (vietvoicetts/core/tts_engine.py:30): prompt PCM, its log-mel and ref_signal_len stay in HBM
  *   vv_get_tensor / vv_set_noise  <- numpy arrays handed between session.run calls (tts_engine.py:229-235)
  *   vv_last_error        <- the exception text wrapped at tts_engine.py:256-257 / model.py:125-129
  *
@@ -80,6 +84,22 @@ int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t n_samples,
                   int64_t n_ids, const float* noise_or_null, uint64_t seed, uint64_t chunk_key,
                   int64_t* ref_len_out);
 
+/* ---- device-resident prompts ------------------------------------------------------------------------------ */
+/* Every prompt the engine sees (vv_preprocess, vv_synthesize_batch, vv_prompt_put) is keyed by a 128-bit content hash
+ * of its PCM and kept in HBM together with its log-mel and ref_signal_len, in an LRU of VVB200_PROMPT_CACHE entries
+ * (default 64; 0 disables caching): all chunks of a long text and all requests for one voice share ONE upload and ONE
+ * mel computation.  vv_prompt_put makes a prompt resident ahead of time and returns its id (never 0);
+ * vv_preprocess_prompt is vv_preprocess for a resident prompt (no audio argument, no hashing); it fails with
+ * VV_ERR_STATE if the prompt has been evicted.  vv_prompt_cache_stats: what[0] = prompts resident, what[1] = uploads
+ * (misses) so far, what[2] = hits so far. */
+int vv_prompt_put(vv_engine* e, const int16_t* audio, int64_t n_samples, uint64_t* prompt_id_out,
+                  int64_t* ref_len_out);
+int vv_prompt_drop(vv_engine* e, uint64_t prompt_id);
+int vv_prompt_cache_clear(vv_engine* e);
+int vv_prompt_cache_stats(vv_engine* e, int64_t* what);
+int vv_preprocess_prompt(vv_batch* b, int idx, uint64_t prompt_id, const int32_t* text_ids, int64_t n_ids,
+                         const float* noise_or_null, uint64_t seed, uint64_t chunk_key, int64_t* ref_len_out);
+
 /* Run `n_steps` Euler steps of the sampler starting at step index `first_step` on the nfe-point time grid
  * (nfe <= 0: the arch default).  n_steps = nfe-1 with first_step = 0 is the whole loop and is replayed from a
  * CUDA graph; n_steps = 1 is one `transformer` session call.  Asynchronous on the engine stream. */
@@ -117,6 +137,8 @@ typedef struct vv_request {
   int16_t* pcm_out;         /* capacity pcm_capacity samples                            */
   int64_t pcm_capacity;
   int64_t n_out;            /* written by the call                                      */
+  uint64_t prompt_id;       /* id from vv_prompt_put, or 0: the prompt is found by hashing `audio`; with a
+                               resident id `audio` may be NULL                          */
 } vv_request;
 /* Synchronous: returns when every pcm_out is filled.  Thread-safe on one engine (calls are serialised by the engine's
  * own lock, like every other entry point; vv_last_error is per thread).  Batches are cached per tuple of total_frames
@@ -131,6 +153,9 @@ int vv_run_resident(vv_batch* b, int nfe);
 /* One eager DiT step with CUDA events around every launch; ms_out[8] = milliseconds per kernel class:
  * 0 qkv GEMM, 1 out-proj GEMM, 2 ffn-up GEMM, 3 ffn-down GEMM, 4 attention, 5 LN-modulate, 6 conv_pos, 7 rest. */
 int vv_profile_step(vv_batch* b, int nfe, int step, float* ms_out);
+/* The resident path with CUDA events at the stage boundaries; ms_out[4] = preprocess (mel of the distinct prompts,
+ * text ConvNeXt, conditioning projection) | sampling loop | decode (Vocos + iSTFT) | whole call.  Synchronous. */
+int vv_profile_stages(vv_batch* b, int nfe, float* ms_out);
 
 /* ---- kernel-level entry points (device pointers; used by the parity tests and micro-benchmarks) ---------- */
 typedef struct vv_gemm_epilogue {

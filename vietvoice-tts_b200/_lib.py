@@ -25,7 +25,8 @@ _lib = None
 class VVRequest(C.Structure):
     _fields_ = [("audio", C.c_void_p), ("n_samples", C.c_int64), ("text_ids", C.c_void_p), ("n_ids", C.c_int64),
                 ("total_frames", C.c_int64), ("noise", C.c_void_p), ("chunk_key", C.c_uint64),
-                ("pcm_out", C.c_void_p), ("pcm_capacity", C.c_int64), ("n_out", C.c_int64)]
+                ("pcm_out", C.c_void_p), ("pcm_capacity", C.c_int64), ("n_out", C.c_int64),
+                ("prompt_id", C.c_uint64)]
 
 
 class VVGemmEpilogue(C.Structure):
@@ -77,6 +78,11 @@ def load() -> C.CDLL:
             "vv_batch_create": (I, [P, I, C.POINTER(I64), C.POINTER(P)]),
             "vv_batch_destroy": (None, [P]),
             "vv_preprocess": (I, [P, I, P, I64, P, I64, P, U64, U64, C.POINTER(I64)]),
+            "vv_prompt_put": (I, [P, P, I64, C.POINTER(U64), C.POINTER(I64)]),
+            "vv_prompt_drop": (I, [P, U64]),
+            "vv_prompt_cache_clear": (I, [P]),
+            "vv_prompt_cache_stats": (I, [P, C.POINTER(I64)]),
+            "vv_preprocess_prompt": (I, [P, I, U64, P, I64, P, U64, U64, C.POINTER(I64)]),
             "vv_sample": (I, [P, I, I, I]),
             "vv_decode": (I, [P, I, P, I64, C.POINTER(I64)]),
             "vv_decode_all": (I, [P, C.POINTER(P), C.POINTER(I64)]),
@@ -90,6 +96,7 @@ def load() -> C.CDLL:
             "vv_synthesize_batch": (I, [P, C.POINTER(VVRequest), I, I, U64]),
             "vv_run_resident": (I, [P, I]),
             "vv_profile_step": (I, [P, I, I, C.POINTER(C.c_float)]),
+            "vv_profile_stages": (I, [P, I, C.POINTER(C.c_float)]),
             "vv_gemm_bf16": (I, [P, P, I, P, I, I, I, I, C.POINTER(VVGemmEpilogue), I]),
             "vv_conv_rows_bf16": (I, [P, P, I, P, I, I, I, C.POINTER(VVGemmEpilogue)]),
             "vv_attention_bf16": (I, [P, P, P, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), I, I]),

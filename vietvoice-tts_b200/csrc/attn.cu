@@ -360,11 +360,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 }
 
 void launch_attention_impl(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM);
-    attr_set = true;
-  }
+  static DeviceOnce attr;
+  attr.once([] { cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM); });
   if (p.n_tiles <= 0) return;
   launch_k(attn_kernel, p.n_tiles * p.heads, attn::THREADS, attn::SMEM, st, tmQKV, p);
 }

@@ -231,11 +231,8 @@ bool conv_pos_supported(const GemmShape& s, const GemmEpi& e) {
 void launch_conv_pos(const CUtensorMap& tmA128, const CUtensorMap& tmA32, const CUtensorMap& tmB, const GemmShape& s,
                      const GemmEpi& e, int num_sms, cudaStream_t st) {
   using namespace convk;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    attr_set = true;
-  }
+  static DeviceOnce attr;
+  attr.once([] { cudaFuncSetAttribute(conv_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); });
   int grid = ((s.M + ROWS - 1) / ROWS) * s.conv_groups;
   if (grid > num_sms) grid = num_sms;
   if (grid < 1) return;

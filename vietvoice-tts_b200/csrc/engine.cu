@@ -15,7 +15,9 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -60,6 +62,27 @@ struct ModTable {
   float* blocks = nullptr;  // [steps][depth][6*dim]
   float* fin = nullptr;     // [steps][2*dim]
   std::vector<float> dt;    // [steps]
+  uint64_t last_use = 0;
+};
+
+// A reference prompt resident in HBM: PCM, its log-mel and ref_signal_len, keyed by a content
+// hash.  All chunks of one long text — and every request for the same voice — share ONE prompt
+// (/root/reference/vietvoicetts/core/tts_engine.py:225-238 feeds the same audio to every chunk;
+// core/model.py:204-211 re-reads it from the tar per request), so it is uploaded and its mel computed once.
+struct Prompt {
+  uint64_t id = 0, check = 0;     // two independent 64-bit content hashes
+  int64_t n_samples = 0;
+  int ref_len = 0;                // n_samples / hop + 1 mel frames
+  int16_t* pcm = nullptr;
+  float* mel = nullptr;           // [ref_len, n_mel]
+  float* scale = nullptr;         // RMS normalisation factor (device scalar)
+  cudaStream_t st = nullptr;
+  uint64_t last_use = 0;
+  ~Prompt() {
+    if (pcm) cudaFreeAsync(pcm, st);
+    if (mel) cudaFreeAsync(mel, st);
+    if (scale) cudaFreeAsync(scale, st);
+  }
 };
 
 struct GemmOp {
@@ -95,7 +118,15 @@ struct vv_engine {
   float2* fft_tw = nullptr;
   float* hann = nullptr;
   float* pos_table = nullptr;
+  // per-NFE time-embedding / AdaLN modulation tables: a small LRU (VVB200_MOD_TABLES, default 4) — a table costs
+  // (nfe-1) * depth * 6 * dim * 4 bytes (0.54 MB per step at full size) and a request stream may sweep nfe
   std::map<int, ModTable> mod;
+  uint64_t mod_tick = 0;
+  std::set<vv_batch*> live;       // every batch of this engine (cached or caller-owned)
+  // device-resident prompts, LRU of VVB200_PROMPT_CACHE entries (default 64; 0 disables caching)
+  std::map<uint64_t, std::shared_ptr<Prompt>> prompts;
+  uint64_t prompt_tick = 0;
+  int64_t prompt_uploads = 0, prompt_hits = 0;
   // bf16 weights
   bf16 *in_n = nullptr, *in_c = nullptr, *c1 = nullptr, *c2 = nullptr, *out_w = nullptr;
   int Kn = 128, Kc = 0, Kemb = 0;
@@ -142,7 +173,8 @@ struct vv_batch {
   int32_t* ids_h = nullptr;             // pinned staging for the id upload
   size_t ids_h_bytes = 0;
   float* noise0 = nullptr;              // y0 as preprocessed (restored by vv_run_resident)
-  std::vector<int64_t> n_samples;
+  std::vector<std::shared_ptr<Prompt>> prompt;   // per chunk: the resident prompt its mel rows come from
+  std::vector<cudaEvent_t> ids_ev;               // per chunk: the H2D copy that last read this chunk's id staging
   std::vector<int> dec_ref_len;         // ref_len snapshot the cached decode layout was built for
   std::vector<GemmOp> dec_ops;
   // DiT buffers
@@ -158,14 +190,13 @@ struct vv_batch {
   std::vector<int> dec_off, dec_len;
   std::vector<int64_t> pcm_off, pcm_len;
   int32_t *d_src_row = nullptr, *d_row_pos = nullptr, *d_row_len = nullptr;
+  int32_t *d_dec_off = nullptr, *d_dec_len = nullptr;
+  int64_t* d_pcm_off = nullptr;
   bf16 *v_emb = nullptr, *v_hb = nullptr, *v_ffb = nullptr;
-  float *vx = nullptr, *v_tmp = nullptr, *v_head = nullptr, *frames = nullptr;
+  float *vx = nullptr, *v_tmp = nullptr, *v_head = nullptr;
   int ld_head = 0;
   int16_t* pcm_d = nullptr;
   int64_t pcm_total = 0;
-  float* scale_tmp = nullptr;
-  std::vector<int16_t*> audio_d;
-  std::vector<int64_t> audio_cap;
   // ops
   GemmOp op_in, op_cond, op_c1, op_c2, op_fin;
   std::vector<GemmOp> op_qkv, op_out, op_ff1, op_ff2, op_tpw1, op_tpw2, op_vpw1, op_vpw2;
@@ -412,8 +443,19 @@ extern "C" int vv_engine_load_blob(vv_engine* e, const void* blob, size_t nbytes
     BlobEntry en;
     memcpy(&en, p + 256 + (size_t)i * sizeof(BlobEntry), sizeof(BlobEntry));
     en.name[95] = 0;
-    if (en.dtype != 0 || en.ndim > 4 || en.offset + en.nbytes > nbytes || (en.nbytes & 3))
+    // offset / size are untrusted: the comparison must not wrap in uint64
+    if (en.dtype != 0 || en.ndim > 4 || en.offset > nbytes || en.nbytes > nbytes - en.offset || (en.nbytes & 3))
       return fail(VV_ERR_FORMAT, "blob entry '%s' malformed", en.name);
+    uint64_t prod = 1;
+    for (uint32_t k = 0; k < en.ndim; ++k) {
+      if (en.shape[k] <= 0 || (uint64_t)en.shape[k] > (1ull << 32) || prod > (1ull << 40))
+        return fail(VV_ERR_FORMAT, "blob entry '%s': bad shape", en.name);
+      prod *= (uint64_t)en.shape[k];
+    }
+    if (prod * 4 != en.nbytes)
+      return fail(VV_ERR_FORMAT, "blob entry '%s': shape holds %llu elements, payload %llu bytes", en.name,
+                  (unsigned long long)prod, (unsigned long long)en.nbytes);
+    if (e->w.count(en.name)) return fail(VV_ERR_FORMAT, "blob entry '%s' loaded twice", en.name);
     WTensor t;
     t.ndim = en.ndim;
     t.numel = en.nbytes / 4;
@@ -455,13 +497,50 @@ static int load_convnext(vv_engine* e, const std::string& p, int d, int ff, bool
   return 0;
 }
 
+static constexpr int VV_MAX_NFE = 256;
+
+static void destroy_batch_graph(vv_batch* b, int nfe);
+
+// Drops the least recently used modulation table other than `keep_nfe`.  Captured sampling-loop graphs hold pointers
+// into the table, so every batch's graph for that nfe and the shared executables go with it.
+static bool evict_mod_table(vv_engine* e, int keep_nfe) {
+  auto victim = e->mod.end();
+  for (auto it = e->mod.begin(); it != e->mod.end(); ++it)
+    if (it->first != keep_nfe && it->first != e->a.nfe &&
+        (victim == e->mod.end() || it->second.last_use < victim->second.last_use))
+      victim = it;
+  if (victim == e->mod.end()) return false;
+  const int nfe = victim->first;
+  cudaStreamSynchronize(e->st);
+  for (vv_batch* b : e->live) destroy_batch_graph(b, nfe);
+  for (auto le = e->loop_exec.begin(); le != e->loop_exec.end();) {
+    if (le->first.first == nfe) {
+      if (le->second.exec) cudaGraphExecDestroy(le->second.exec);
+      le = e->loop_exec.erase(le);
+    } else {
+      ++le;
+    }
+  }
+  cudaFree(victim->second.blocks);
+  cudaFree(victim->second.fin);
+  e->mod.erase(victim);
+  return true;
+}
+
 static int build_mod_table(vv_engine* e, int nfe, ModTable** out) {
   auto it = e->mod.find(nfe);
   if (it != e->mod.end()) {
+    it->second.last_use = ++e->mod_tick;
     *out = &it->second;
     return 0;
   }
-  if (nfe < 2 || nfe > 1024) return fail(VV_ERR_ARG, "nfe %d out of range", nfe);
+  if (nfe < 2 || nfe > VV_MAX_NFE) return fail(VV_ERR_ARG, "nfe %d out of range [2, %d]", nfe, VV_MAX_NFE);
+  static const size_t cap = [] {
+    const char* v = getenv("VVB200_MOD_TABLES");
+    const int n = v ? atoi(v) : 4;
+    return (size_t)(n < 1 ? 1 : n);
+  }();
+  while (e->mod.size() >= cap && evict_mod_table(e, nfe)) {}
   const vv_arch& a = e->a;
   ModTable mt;
   mt.nfe = nfe;
@@ -483,12 +562,23 @@ static int build_mod_table(vv_engine* e, int nfe, ModTable** out) {
       emb[(size_t)i * a.time_freq_dim + half + k] = (float)cos(ang);
     }
   }
+  // the table owns `blocks` / `fin` (freed on eviction); the three scratch buffers are released below
+  std::vector<void*> own, scratch;
+  struct Guard {
+    std::vector<void*>&own, &scratch;
+    bool keep = false;
+    ~Guard() {
+      for (void* q : scratch) cudaFree(q);
+      if (!keep)
+        for (void* q : own) cudaFree(q);
+    }
+  } guard{own, scratch};
   float *emb_d, *h1, *st;
-  TRY(dev_alloc(e->allocs, &emb_d, emb.size()));
-  TRY(dev_alloc(e->allocs, &h1, (size_t)S * a.dim));
-  TRY(dev_alloc(e->allocs, &st, (size_t)S * a.dim));
-  TRY(dev_alloc(e->allocs, &mt.blocks, (size_t)S * a.depth * 6 * a.dim));
-  TRY(dev_alloc(e->allocs, &mt.fin, (size_t)S * 2 * a.dim));
+  TRY(dev_alloc(scratch, &emb_d, emb.size()));
+  TRY(dev_alloc(scratch, &h1, (size_t)S * a.dim));
+  TRY(dev_alloc(scratch, &st, (size_t)S * a.dim));
+  TRY(dev_alloc(own, &mt.blocks, (size_t)S * a.depth * 6 * a.dim));
+  TRY(dev_alloc(own, &mt.fin, (size_t)S * 2 * a.dim));
   CK(cudaMemcpyAsync(emb_d, emb.data(), emb.size() * 4, cudaMemcpyHostToDevice, e->st));
   const float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   TRY(need_w(e, "dit.time.l1.w", &w1, (size_t)a.dim * a.time_freq_dim));
@@ -513,6 +603,8 @@ static int build_mod_table(vv_engine* e, int nfe, ModTable** out) {
   e->launches++;
   CK(cudaStreamSynchronize(e->st));
   CKL();
+  guard.keep = true;
+  mt.last_use = ++e->mod_tick;
   e->mod[nfe] = mt;
   *out = &e->mod[nfe];
   return 0;
@@ -589,7 +681,23 @@ extern "C" void vv_engine_destroy(vv_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
-  for (auto& kv : e->batch_cache) vv_batch_destroy(kv.second);
+  {
+    ENG_LOCK(e);
+    {
+      std::vector<vv_batch*> cached;
+      for (auto& kv : e->batch_cache) cached.push_back(kv.second);
+      for (vv_batch* cb : cached) vv_batch_destroy(cb);     // each removes itself from the cache
+    }
+    e->batch_cache.clear();
+    for (vv_batch* b : e->live) b->e = nullptr;     // caller-owned batches outliving the engine: destroy is a no-op
+    e->live.clear();
+    e->prompts.clear();
+    for (auto& m : e->mod) {
+      cudaFree(m.second.blocks);
+      cudaFree(m.second.fin);
+    }
+  }
+  cudaStreamSynchronize(e->st);
   for (void* p : e->allocs) cudaFree(p);
   for (auto& pf : e->pinned_free) cudaFreeHost(pf.second);
   for (auto& le : e->loop_exec)
@@ -608,9 +716,10 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   vv_batch* b = new vv_batch();
   b->e = e;
   b->B = B;
+  e->live.insert(b);
   const int gap = 16;  // >= conv_pos_k/2 zero rows between sequences
   if (a.conv_pos_k / 2 > gap) {
-    delete b;
+    vv_batch_destroy(b);
     return fail(VV_ERR_ARG, "conv_pos_k too large for the row layout");
   }
   b->T.resize(B);
@@ -621,7 +730,7 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   int R = 0;
   for (int i = 0; i < B; ++i) {
     if (total_frames[i] < 2 || total_frames[i] > e->rope_max) {
-      delete b;
+      vv_batch_destroy(b);
       return fail(VV_ERR_ARG, "total_frames[%d] = %lld out of range [2, %d]", i, (long long)total_frames[i], e->rope_max);
     }
     b->T[i] = (int)total_frames[i];
@@ -692,7 +801,8 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
       b->ids_h_bytes = bytes;
     }
   }
-  b->n_samples.assign(B, 0);
+  b->prompt.assign(B, nullptr);
+  b->ids_ev.assign(B, nullptr);
   AB(b->noise, (size_t)R * a.n_mel);
   AB(b->mel, (size_t)R * a.n_mel);
   AB(b->cond_proj, (size_t)M * d);
@@ -715,7 +825,6 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   AB(b->nx, (size_t)2 * B * a.text_ff);
   AB(b->t_hb, (size_t)M * a.text_dim);
   AB(b->t_ffb, (size_t)M * a.text_ff);
-  AB(b->scale_tmp, 16);
   // decode
   int rd = 0;
   for (int i = 0; i < B; ++i) rd += b->T[i];
@@ -730,10 +839,10 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   AB(b->vx, (size_t)b->Rd_max * a.voc_dim);
   AB(b->v_tmp, (size_t)b->Rd_max * a.voc_dim);
   AB(b->v_head, (size_t)b->Rd_max * b->ld_head);
-  AB(b->frames, (size_t)b->Rd_max * 1024);
+  AB(b->d_dec_off, B);
+  AB(b->d_dec_len, B);
+  AB(b->d_pcm_off, B);
   AB(b->pcm_d, (size_t)b->Rd_max * a.hop);
-  b->audio_d.assign(B, nullptr);
-  b->audio_cap.assign(B, 0);
   b->dec_off.assign(B, 0);
   b->dec_len.assign(B, 0);
   b->pcm_off.assign(B, 0);
@@ -762,30 +871,189 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   return 0;
 }
 
+static void destroy_batch_graph(vv_batch* b, int nfe) {
+  auto it = b->graphs.find(nfe);
+  if (it == b->graphs.end()) return;
+  cudaGraphDestroy(it->second);
+  b->graphs.erase(it);
+  b->graph_launches.erase(nfe);
+}
+
 extern "C" void vv_batch_destroy(vv_batch* b) {
   if (!b) return;
-  cudaSetDevice(b->e->device);
-  cudaStreamSynchronize(b->e->st);
+  vv_engine* e = b->e;
+  if (!e) {            // the engine went first (vv_engine_destroy): its stream and pool are gone, only host state is left
+    delete b;
+    return;
+  }
+  // Python reaches this from Batch.__del__ / cache eviction on any thread while another thread may be inside
+  // vv_synthesize_batch: every entry point that touches engine state takes the (recursive) engine lock
+  ENG_LOCK(e);
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
   for (auto& g : b->graphs) cudaGraphDestroy(g.second);
-  for (auto& le : b->e->loop_exec)
+  for (auto& le : e->loop_exec)
     if (le.second.owner == b) le.second.owner = nullptr;     // the executable must be updated before its next launch
-  for (void* p : b->allocs) cudaFreeAsync(p, b->e->st);     // back to the pool, no device-wide synchronisation
-  for (int16_t* p : b->audio_d)
-    if (p) cudaFreeAsync(p, b->e->st);
-  if (b->ids_h) b->e->pinned_free.emplace_back(b->ids_h_bytes, b->ids_h);   // pinned staging buffers are recycled
+  for (void* p : b->allocs) cudaFreeAsync(p, e->st);        // back to the pool, no device-wide synchronisation
+  for (cudaEvent_t ev : b->ids_ev)
+    if (ev) cudaEventDestroy(ev);
+  b->prompt.clear();                                         // resident prompts are shared: last owner frees them
+  if (b->ids_h) e->pinned_free.emplace_back(b->ids_h_bytes, b->ids_h);   // pinned staging buffers are recycled
+  e->live.erase(b);
+  e->batch_last_use.erase(b);
+  for (auto it = e->batch_cache.begin(); it != e->batch_cache.end(); ++it)
+    if (it->second == b) {
+      e->batch_cache.erase(it);
+      break;
+    }
   delete b;
 }
 
-// device part of the preprocess graph for chunk idx: log-mel of the resident prompt, y0 -> bf16 operand
+// ------------------------------------------------------------------------------------------------ resident prompts
+// Two independent 64-bit content hashes of the PCM (4 interleaved multiply-xorshift lanes each; ~10 GB/s on the host).
+static void hash_pcm(const int16_t* audio, int64_t n, uint64_t* id, uint64_t* check) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(audio);
+  const size_t bytes = (size_t)n * 2;
+  uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+  uint64_t g[4] = {0xD6E8FEB86659FD93ull, 0xA0761D6478BD642Full, 0xE7037ED1A0B428DBull, 0x8EBC6AF09C88C6E3ull};
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    for (int k = 0; k < 4; ++k) {
+      h[k] = (h[k] ^ w[k]) * 0x9FB21C651E98DF25ull;
+      h[k] ^= h[k] >> 29;
+      g[k] = (g[k] + w[k]) * 0xFF51AFD7ED558CCDull;
+      g[k] ^= g[k] >> 31;
+    }
+  }
+  uint64_t tail[4] = {0, 0, 0, 0};
+  memcpy(tail, p + i, bytes - i);
+  for (int k = 0; k < 4; ++k) {
+    h[k] = (h[k] ^ tail[k]) * 0x9FB21C651E98DF25ull;
+    g[k] = (g[k] + tail[k]) * 0xFF51AFD7ED558CCDull;
+  }
+  uint64_t a = (uint64_t)bytes * 0x9E3779B97F4A7C15ull, c = ~(uint64_t)bytes;
+  for (int k = 0; k < 4; ++k) {
+    a = (a ^ h[k]) * 0xC4CEB9FE1A85EC53ull;
+    a ^= a >> 32;
+    c = (c + g[k]) * 0xBF58476D1CE4E5B9ull;
+    c ^= c >> 30;
+  }
+  *id = a ? a : 1;      // 0 means "no prompt id" in vv_request
+  *check = c;
+}
+
+static size_t prompt_cache_cap() {
+  static const size_t cap = [] {
+    const char* v = getenv("VVB200_PROMPT_CACHE");
+    const int n = v ? atoi(v) : 64;
+    return (size_t)(n < 0 ? 0 : n);
+  }();
+  return cap;
+}
+
+// log-mel of a resident prompt (all ref_len frames), recomputed in place
+static void prompt_mel(vv_engine* e, Prompt* pr) {
+  const vv_arch& a = e->a;
+  const WTensor* fb = find_w(e, "pre.mel_fb");
+  launch_mel(pr->pcm, pr->n_samples, a.target_rms, pr->scale, e->hann, e->fft_tw, fb->d, a.n_mel, a.mel_clamp,
+             pr->ref_len, pr->mel, e->st);
+  e->launches += 2;
+}
+
+// Returns the resident prompt for this PCM, uploading it and computing its mel if it is not cached.
+static int prompt_acquire(vv_engine* e, const int16_t* audio, int64_t n_samples, std::shared_ptr<Prompt>* out) {
+  const vv_arch& a = e->a;
+  if (!audio) return fail(VV_ERR_ARG, "prompt audio is null");
+  if (n_samples < a.n_fft / 2 + 1) return fail(VV_ERR_ARG, "prompt audio too short (%lld samples)", (long long)n_samples);
+  if (n_samples / a.hop + 1 > e->rope_max) return fail(VV_ERR_ARG, "prompt audio too long (%lld samples)", (long long)n_samples);
+  uint64_t id, check;
+  hash_pcm(audio, n_samples, &id, &check);
+  auto it = e->prompts.find(id);
+  if (it != e->prompts.end() && it->second->check == check && it->second->n_samples == n_samples) {
+    it->second->last_use = ++e->prompt_tick;
+    e->prompt_hits++;
+    *out = it->second;
+    return 0;
+  }
+  auto pr = std::make_shared<Prompt>();
+  pr->id = id;
+  pr->check = check;
+  pr->n_samples = n_samples;
+  pr->ref_len = (int)(n_samples / a.hop) + 1;
+  pr->st = e->st;
+  CK(cudaMallocAsync(&pr->pcm, (size_t)n_samples * 2, e->st));
+  CK(cudaMallocAsync(&pr->mel, (size_t)pr->ref_len * a.n_mel * 4, e->st));
+  CK(cudaMallocAsync(&pr->scale, 16, e->st));
+  CK(cudaMemcpyAsync(pr->pcm, audio, (size_t)n_samples * 2, cudaMemcpyHostToDevice, e->st));
+  prompt_mel(e, pr.get());
+  e->prompt_uploads++;
+  pr->last_use = ++e->prompt_tick;
+  const size_t cap = prompt_cache_cap();
+  if (cap > 0) {
+    while (e->prompts.size() >= cap) {           // LRU: batches that still use an evicted prompt keep it alive
+      auto victim = e->prompts.begin();
+      for (auto c = e->prompts.begin(); c != e->prompts.end(); ++c)
+        if (c->second->last_use < victim->second->last_use) victim = c;
+      e->prompts.erase(victim);
+    }
+    e->prompts[id] = pr;
+  }
+  *out = pr;
+  return 0;
+}
+
+extern "C" int vv_prompt_put(vv_engine* e, const int16_t* audio, int64_t n_samples, uint64_t* prompt_id_out,
+                             int64_t* ref_len_out) {
+  if (!e || !prompt_id_out) return fail(VV_ERR_ARG, "vv_prompt_put: bad argument");
+  ENG_LOCK(e);
+  if (!e->finalized) return fail(VV_ERR_STATE, "engine not finalized");
+  CK(cudaSetDevice(e->device));
+  std::shared_ptr<Prompt> pr;
+  TRY(prompt_acquire(e, audio, n_samples, &pr));
+  if (prompt_cache_cap() == 0) return fail(VV_ERR_STATE, "prompt cache disabled (VVB200_PROMPT_CACHE=0)");
+  CKL();
+  *prompt_id_out = pr->id;
+  if (ref_len_out) *ref_len_out = pr->ref_len;
+  return 0;
+}
+
+extern "C" int vv_prompt_drop(vv_engine* e, uint64_t prompt_id) {
+  if (!e) return fail(VV_ERR_ARG, "null engine");
+  ENG_LOCK(e);
+  CK(cudaSetDevice(e->device));
+  return e->prompts.erase(prompt_id) ? 0 : fail(VV_ERR_ARG, "prompt %llu is not resident", (unsigned long long)prompt_id);
+}
+
+extern "C" int vv_prompt_cache_clear(vv_engine* e) {
+  if (!e) return fail(VV_ERR_ARG, "null engine");
+  ENG_LOCK(e);
+  CK(cudaSetDevice(e->device));
+  e->prompts.clear();
+  return 0;
+}
+
+/* what[0] = prompts resident, what[1] = uploads (misses) so far, what[2] = hits so far */
+extern "C" int vv_prompt_cache_stats(vv_engine* e, int64_t* what) {
+  if (!e || !what) return fail(VV_ERR_ARG, "vv_prompt_cache_stats: bad argument");
+  ENG_LOCK(e);
+  what[0] = (int64_t)e->prompts.size();
+  what[1] = e->prompt_uploads;
+  what[2] = e->prompt_hits;
+  return 0;
+}
+
+// device part of the preprocess graph for chunk idx: the prompt's resident log-mel -> rows of the batch, y0 -> bf16
 static int preprocess_device(vv_batch* b, int idx) {
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
   const int T = b->T[idx], off = b->seq_off[idx];
-  CK(cudaMemsetAsync(b->mel + (size_t)off * a.n_mel, 0, (size_t)T * a.n_mel * 4, e->st));
-  const WTensor* fb = find_w(e, "pre.mel_fb");
-  launch_mel(b->audio_d[idx], b->n_samples[idx], a.target_rms, b->scale_tmp + (idx & 15), e->hann, e->fft_tw, fb->d,
-             a.n_mel, a.mel_clamp, std::min(b->ref_len[idx], T), b->mel + (size_t)off * a.n_mel, e->st);
-  e->launches += 2;
+  const Prompt* pr = b->prompt[idx].get();
+  const int rows = std::min(pr->ref_len, T);
+  float* dst = b->mel + (size_t)off * a.n_mel;
+  CK(cudaMemcpyAsync(dst, pr->mel, (size_t)rows * a.n_mel * 4, cudaMemcpyDeviceToDevice, e->st));
+  if (T > rows) CK(cudaMemsetAsync(dst + (size_t)rows * a.n_mel, 0, (size_t)(T - rows) * a.n_mel * 4, e->st));
   float* nz = b->noise + (size_t)off * a.n_mel;
   launch_noise_to_bf16(nz, T, a.n_mel, b->noise_b + (size_t)off * e->Kn, b->noise_b + (size_t)(b->R + off) * e->Kn,
                        e->Kn, e->st);
@@ -793,34 +1061,26 @@ static int preprocess_device(vv_batch* b, int idx) {
   return 0;
 }
 
-extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t n_samples, const int32_t* text_ids,
-                             int64_t n_ids, const float* noise_or_null, uint64_t seed, uint64_t chunk_key,
-                             int64_t* ref_len_out) {
-  if (!b || !audio || idx < 0 || idx >= b->B || n_ids < 0 || (n_ids > 0 && !text_ids))
-    return fail(VV_ERR_ARG, "vv_preprocess: bad argument");
-  ENG_LOCK(b->e);
+// everything of vv_preprocess after the prompt has been resolved
+static int preprocess_chunk(vv_batch* b, int idx, std::shared_ptr<Prompt> pr, const int32_t* text_ids, int64_t n_ids,
+                            const float* noise_or_null, uint64_t seed, uint64_t chunk_key, int64_t* ref_len_out) {
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
-  if (n_samples < a.n_fft / 2 + 1) return fail(VV_ERR_ARG, "prompt audio too short (%lld samples)", (long long)n_samples);
-  CK(cudaSetDevice(e->device));
   const int T = b->T[idx], off = b->seq_off[idx];
-  const int ref_len = (int)(n_samples / a.hop) + 1;
   // text ids: +1, truncated / zero padded to T (uncond rows stay 0); validated before any state changes
   for (int i = 0; i < T && i < n_ids; ++i)
     if (text_ids[i] < 0 || text_ids[i] >= a.vocab) return fail(VV_ERR_ARG, "text id %d out of vocabulary range", text_ids[i]);
-  b->ref_len[idx] = ref_len;
-  b->n_samples[idx] = n_samples;
-  if (ref_len_out) *ref_len_out = ref_len;
-  if (b->audio_cap[idx] < n_samples) {
-    if (b->audio_d[idx]) CK(cudaFreeAsync(b->audio_d[idx], e->st));
-    b->audio_d[idx] = nullptr;
-    CK(cudaMallocAsync(&b->audio_d[idx], (size_t)n_samples * 2, e->st));
-    b->audio_cap[idx] = n_samples;
-  }
-  CK(cudaMemcpyAsync(b->audio_d[idx], audio, (size_t)n_samples * 2, cudaMemcpyHostToDevice, e->st));
+  b->prompt[idx] = pr;
+  b->ref_len[idx] = pr->ref_len;
+  if (ref_len_out) *ref_len_out = pr->ref_len;
+  // the pinned staging slice of this chunk may still be read by the H2D copy of an earlier vv_preprocess of the same
+  // chunk (no host sync in between): wait for that copy before overwriting it
+  if (b->ids_ev[idx]) CK(cudaEventSynchronize(b->ids_ev[idx]));
+  else CK(cudaEventCreateWithFlags(&b->ids_ev[idx], cudaEventDisableTiming));
   int32_t* stage = b->ids_h + off;
   for (int i = 0; i < T; ++i) stage[i] = i < n_ids ? text_ids[i] + 1 : 0;
   CK(cudaMemcpyAsync(b->ids_d + off, stage, (size_t)T * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaEventRecord(b->ids_ev[idx], e->st));
   float* nz = b->noise + (size_t)off * a.n_mel;
   if (noise_or_null) {
     CK(cudaMemcpyAsync(nz, noise_or_null, (size_t)T * a.n_mel * 4, cudaMemcpyHostToDevice, e->st));
@@ -836,6 +1096,35 @@ extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t
   b->decoded = false;
   b->steps_done = 0;
   return 0;
+}
+
+extern "C" int vv_preprocess(vv_batch* b, int idx, const int16_t* audio, int64_t n_samples, const int32_t* text_ids,
+                             int64_t n_ids, const float* noise_or_null, uint64_t seed, uint64_t chunk_key,
+                             int64_t* ref_len_out) {
+  if (!b || !b->e || !audio || idx < 0 || idx >= b->B || n_ids < 0 || (n_ids > 0 && !text_ids))
+    return fail(VV_ERR_ARG, "vv_preprocess: bad argument");
+  ENG_LOCK(b->e);
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  std::shared_ptr<Prompt> pr;
+  TRY(prompt_acquire(e, audio, n_samples, &pr));
+  return preprocess_chunk(b, idx, pr, text_ids, n_ids, noise_or_null, seed, chunk_key, ref_len_out);
+}
+
+extern "C" int vv_preprocess_prompt(vv_batch* b, int idx, uint64_t prompt_id, const int32_t* text_ids, int64_t n_ids,
+                                    const float* noise_or_null, uint64_t seed, uint64_t chunk_key,
+                                    int64_t* ref_len_out) {
+  if (!b || !b->e || idx < 0 || idx >= b->B || n_ids < 0 || (n_ids > 0 && !text_ids))
+    return fail(VV_ERR_ARG, "vv_preprocess_prompt: bad argument");
+  ENG_LOCK(b->e);
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  auto it = e->prompts.find(prompt_id);
+  if (it == e->prompts.end())
+    return fail(VV_ERR_STATE, "prompt %llu is not resident (evicted or never put)", (unsigned long long)prompt_id);
+  it->second->last_use = ++e->prompt_tick;
+  e->prompt_hits++;
+  return preprocess_chunk(b, idx, it->second, text_ids, n_ids, noise_or_null, seed, chunk_key, ref_len_out);
 }
 
 // text ConvNeXt-V2 over all rows, concat, conditioning projection
@@ -1046,21 +1335,58 @@ extern "C" int vv_debug_partial_step(vv_batch* b, int nfe, int step, int n_layer
 
 // Whole path with every input already resident in HBM (prompt PCM, text ids, y0): mel -> text embed -> cond ->
 // (nfe-1) DiT steps -> Vocos/iSTFT -> int16 PCM left on the device.  No host<->device copies, no host sync.
-extern "C" int vv_run_resident(vv_batch* b, int nfe) {
-  if (!b) return fail(VV_ERR_ARG, "null batch");
-  ENG_LOCK(b->e);
+// ev: optional 4 events recorded on the engine stream at the stage boundaries (start | preprocess done | loop done |
+// decode done)
+static int run_resident_impl(vv_batch* b, int nfe, cudaEvent_t* ev) {
   vv_engine* e = b->e;
   const vv_arch& a = e->a;
-  CK(cudaSetDevice(e->device));
   for (int i = 0; i < b->B; ++i)
     if (!b->prepped[i]) return fail(VV_ERR_STATE, "vv_run_resident: chunk %d has not been preprocessed", i);
+  if (ev) CK(cudaEventRecord(ev[0], e->st));
   CK(cudaMemcpyAsync(b->noise, b->noise0, (size_t)b->R * a.n_mel * 4, cudaMemcpyDeviceToDevice, e->st));
+  // the mel front-end runs once per DISTINCT prompt of the batch (chunks of one text share theirs), from resident PCM
+  std::set<const Prompt*> seen;
+  for (int i = 0; i < b->B; ++i)
+    if (seen.insert(b->prompt[i].get()).second) prompt_mel(e, b->prompt[i].get());
   for (int i = 0; i < b->B; ++i) TRY(preprocess_device(b, i));
   b->committed = false;
   b->decoded = false;
   if (nfe <= 0) nfe = a.nfe;
+  TRY(commit(b));
+  if (ev) CK(cudaEventRecord(ev[1], e->st));
   TRY(vv_sample(b, nfe, 0, nfe - 1));
+  if (ev) CK(cudaEventRecord(ev[2], e->st));
   TRY(decode_all(b));
+  if (ev) CK(cudaEventRecord(ev[3], e->st));
+  return 0;
+}
+
+extern "C" int vv_run_resident(vv_batch* b, int nfe) {
+  if (!b || !b->e) return fail(VV_ERR_ARG, "null batch");
+  ENG_LOCK(b->e);
+  CK(cudaSetDevice(b->e->device));
+  return run_resident_impl(b, nfe, nullptr);
+}
+
+// The resident path once more with CUDA events at the stage boundaries: ms_out[0] preprocess (mel of the distinct
+// prompts, text ConvNeXt, conditioning projection), [1] the (nfe-1)-step sampling loop, [2] decode (Vocos + iSTFT),
+// [3] the whole call.  Synchronous.
+extern "C" int vv_profile_stages(vv_batch* b, int nfe, float* ms_out /* [4] */) {
+  if (!b || !b->e || !ms_out) return fail(VV_ERR_ARG, "vv_profile_stages: bad argument");
+  ENG_LOCK(b->e);
+  vv_engine* e = b->e;
+  CK(cudaSetDevice(e->device));
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev[i]));
+  int rc = run_resident_impl(b, nfe, ev);
+  cudaError_t r = cudaStreamSynchronize(e->st);
+  if (rc == 0 && r == cudaSuccess) {
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    cudaEventElapsedTime(&ms_out[3], ev[0], ev[3]);
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  if (rc) return rc;
+  if (r != cudaSuccess) return fail(VV_ERR_CUDA, "vv_profile_stages failed: %s", cudaGetErrorString(r));
   return 0;
 }
 
@@ -1191,6 +1517,13 @@ static int decode_all(vv_batch* b) {
     }
     b->Rd = rd0;
     b->pcm_total = po;
+    {
+      std::vector<int32_t> doff(b->dec_off.begin(), b->dec_off.end()), dlen(b->dec_len.begin(), b->dec_len.end());
+      CK(cudaMemcpyAsync(b->d_dec_off, doff.data(), (size_t)b->B * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(b->d_dec_len, dlen.data(), (size_t)b->B * 4, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(b->d_pcm_off, b->pcm_off.data(), (size_t)b->B * 8, cudaMemcpyHostToDevice, e->st));
+      CK(cudaStreamSynchronize(e->st));
+    }
     if (rd0 > 0) {
       CK(cudaMemcpyAsync(b->d_src_row, src.data(), (size_t)rd0 * 4, cudaMemcpyHostToDevice, e->st));
       CK(cudaMemcpyAsync(b->d_row_pos, pos.data(), (size_t)rd0 * 4, cudaMemcpyHostToDevice, e->st));
@@ -1249,12 +1582,12 @@ static int decode_all(vv_batch* b) {
   GemmEpi eh;
   eh.bias = hb; eh.out_f32 = b->v_head; eh.ld_f32 = b->ld_head;
   run_gemm(e, oh, eh);
-  for (int i = 0; i < b->B; ++i) {
-    if (b->dec_len[i] <= 0) continue;
-    launch_istft(b->v_head + (size_t)b->dec_off[i] * b->ld_head, b->ld_head, e->hann, e->fft_tw, a.mag_clip,
-                 b->dec_len[i], b->frames + (size_t)b->dec_off[i] * 1024, a.pcm_scale, b->pcm_d + b->pcm_off[i],
-                 b->pcm_len[i], e->st);
-    e->launches += 2;
+  {  // inverse FFT + window + overlap-add + envelope + int16 pack of ALL chunks in one launch; frames stay in smem
+    int max_len = 0;
+    for (int i = 0; i < b->B; ++i) max_len = std::max(max_len, b->dec_len[i]);
+    launch_istft_ola(b->v_head, b->ld_head, e->hann, e->fft_tw, a.mag_clip, b->d_dec_off, b->d_dec_len, b->d_pcm_off,
+                     b->B, max_len, a.pcm_scale, b->pcm_d, e->st);
+    e->launches++;
   }
   CKL();
   b->decoded = true;
@@ -1426,6 +1759,8 @@ extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, cons
 extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed) {
   if (!e || !reqs || B <= 0) return fail(VV_ERR_ARG, "vv_synthesize_batch: bad argument");
   ENG_LOCK(e);
+  if (!e->finalized) return fail(VV_ERR_STATE, "engine not finalized");
+  CK(cudaSetDevice(e->device));
   std::vector<int64_t> key(B);
   for (int i = 0; i < B; ++i) key[i] = reqs[i].total_frames;
   vv_batch* b = nullptr;
@@ -1443,10 +1778,7 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
       for (auto c = e->batch_cache.begin(); c != e->batch_cache.end(); ++c)
         if (victim == e->batch_cache.end() || e->batch_last_use[c->second] < e->batch_last_use[victim->second]) victim = c;
       if (victim == e->batch_cache.end()) return false;
-      cudaStreamSynchronize(e->st);
-      e->batch_last_use.erase(victim->second);
-      vv_batch_destroy(victim->second);
-      e->batch_cache.erase(victim);
+      vv_batch_destroy(victim->second);      // synchronises the stream, removes itself from the cache and the LRU
       return true;
     };
     while (e->batch_cache.size() >= cap && evict_lru()) {}
@@ -1465,8 +1797,15 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
   e->batch_last_use[b] = ++e->batch_tick;
   for (int i = 0; i < B; ++i) {
     int64_t rl;
-    TRY(vv_preprocess(b, i, reqs[i].audio, reqs[i].n_samples, reqs[i].text_ids, reqs[i].n_ids, reqs[i].noise, seed,
-                      reqs[i].chunk_key, &rl));
+    if (reqs[i].prompt_id != 0 && e->prompts.count(reqs[i].prompt_id))
+      TRY(vv_preprocess_prompt(b, i, reqs[i].prompt_id, reqs[i].text_ids, reqs[i].n_ids, reqs[i].noise, seed,
+                               reqs[i].chunk_key, &rl));
+    else if (reqs[i].audio)       // hashed: a prompt shared by several chunks / calls is uploaded once
+      TRY(vv_preprocess(b, i, reqs[i].audio, reqs[i].n_samples, reqs[i].text_ids, reqs[i].n_ids, reqs[i].noise, seed,
+                        reqs[i].chunk_key, &rl));
+    else
+      return fail(VV_ERR_STATE, "request %d: prompt %llu is not resident and no audio was given", i,
+                  (unsigned long long)reqs[i].prompt_id);
   }
   if (nfe <= 0) nfe = e->a.nfe;
   TRY(vv_sample(b, nfe, 0, nfe - 1));

@@ -304,57 +304,85 @@ void launch_voc_im2col(const float* mel, const int32_t* src_row, const int32_t* 
   if (n) voc_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel, src_row, row_pos, row_len, rows, n_mel, K, ld, out);
 }
 
-// one block per frame: head [logmag(513) | phase(513)] -> irFFT-1024 -> * hann -> frames[r, 1024]
+// head [logmag(513) | phase(513)] per frame -> irFFT-1024 -> * hann -> overlap-add -> / window envelope -> trim
+// n_fft/2 -> scale, clamp -> int16 (truncate toward zero), for every chunk of the batch in ONE launch.
+//
+// A block owns OLA_HOPS consecutive output hops (256 samples each) of one chunk.  Output hop h receives frames
+// h-1 .. h+2, so the block inverse-transforms OLA_HOPS + 3 frames in shared memory and accumulates their windowed
+// samples straight into a shared output strip: the 4 KB/frame `frames` array of the two-kernel version never exists
+// (HBM traffic per frame: 1026 fp32 read (x 16/13 for the halo frames) + 256 int16 written).  Frames are visited in
+// DEscending order, which is the order the per-sample loop of the former ola kernel added them in: same bits out.
+constexpr int OLA_HOPS = 13;
 __global__ void __launch_bounds__(256)
-istft_frames_kernel(const float* __restrict__ head, int ld_head, const float* __restrict__ hann,
-                    const float2* __restrict__ tw_g, float mag_clip, float* __restrict__ frames) {
+istft_ola_kernel(const float* __restrict__ head, int ld_head, const float* __restrict__ hann_g,
+                 const float2* __restrict__ tw_g, float mag_clip, const int32_t* __restrict__ dec_off,
+                 const int32_t* __restrict__ dec_len, const int64_t* __restrict__ pcm_off, float pcm_scale,
+                 int16_t* __restrict__ pcm) {
   __shared__ float2 s[1024];
   __shared__ float2 tw[512];
-  const int r = blockIdx.x, tid = threadIdx.x;
+  __shared__ float hann[1024];
+  __shared__ float acc[OLA_HOPS * 256];
+  const int chunk = blockIdx.y, tid = threadIdx.x;
+  const int n_frames = dec_len[chunk];
+  const int n_hops = n_frames - 1;                 // output samples = (n_frames - 1) * 256
+  const int h0 = blockIdx.x * OLA_HOPS;
+  if (h0 >= n_hops) return;
+  const int hops = min(OLA_HOPS, n_hops - h0);
   for (int i = tid; i < 512; i += 256) tw[i] = tw_g[i];
-  const float* hr = head + (size_t)r * ld_head;
-  for (int k = tid; k <= 512; k += 256) {
-    const float mag = fminf(expf(hr[k]), mag_clip);
-    float sn, cs;
-    sincosf(hr[513 + k], &sn, &cs);
-    float2 X = make_float2(mag * cs, mag * sn);
-    if (k == 0 || k == 512) X.y = 0.f;       // irfft ignores Im of DC / Nyquist
-    s[__brev((unsigned)k) >> 22] = X;
-    if (k > 0 && k < 512) s[__brev((unsigned)(1024 - k)) >> 22] = make_float2(X.x, -X.y);
-  }
-  __syncthreads();
-  fft1024(s, tw, true, tid);
-  for (int n = tid; n < 1024; n += 256) frames[(size_t)r * 1024 + n] = s[n].x * (1.0f / 1024.0f) * hann[n];
-}
-
-// overlap-add + window-envelope normalisation + trim n_fft/2 + scale/clamp -> int16 (truncate toward zero)
-__global__ void ola_pcm_kernel(const float* __restrict__ frames, const float* __restrict__ hann, int n_frames,
-                               float pcm_scale, int16_t* __restrict__ pcm, int64_t n_out) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_out) return;
-  const int64_t p = n + 512;
-  const int f_hi = (int)(p >> 8);
-  float acc = 0.f, env = 0.f;
-#pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const int f = f_hi - d;
-    if (f >= 0 && f < n_frames) {
-      const int k = (int)(p - (int64_t)f * 256);
-      acc += frames[(size_t)f * 1024 + k];
-      const float w = hann[k];
-      env += w * w;
+  for (int i = tid; i < 1024; i += 256) hann[i] = hann_g[i];
+  for (int i = tid; i < OLA_HOPS * 256; i += 256) acc[i] = 0.f;
+  const int base = 256 * h0 + 512;                 // padded position of this block's first output sample
+  const int f_lo = max(h0 - 1, 0), f_hi = min(h0 + hops + 1, n_frames - 1);
+  const float* hbase = head + (size_t)dec_off[chunk] * ld_head;
+  for (int f = f_hi; f >= f_lo; --f) {
+    __syncthreads();                               // previous frame's samples consumed, tables / acc initialised
+    const float* hr = hbase + (size_t)f * ld_head;
+    for (int k = tid; k <= 512; k += 256) {
+      const float mag = fminf(expf(hr[k]), mag_clip);
+      float sn, cs;
+      sincosf(hr[513 + k], &sn, &cs);
+      float2 X = make_float2(mag * cs, mag * sn);
+      if (k == 0 || k == 512) X.y = 0.f;           // irfft ignores Im of DC / Nyquist
+      s[__brev((unsigned)k) >> 22] = X;
+      if (k > 0 && k < 512) s[__brev((unsigned)(1024 - k)) >> 22] = make_float2(X.x, -X.y);
+    }
+    __syncthreads();
+    fft1024(s, tw, true, tid);
+    const int shift = 256 * f - base;              // acc index of sample 0 of this frame
+    for (int n = tid; n < 1024; n += 256) {
+      const int i = n + shift;
+      // separate multiply / add roundings (no FMA contraction): bit-identical to summing stored fp32 frames
+      if (i >= 0 && i < hops * 256)
+        acc[i] = __fadd_rn(acc[i], __fmul_rn(__fmul_rn(s[n].x, 1.0f / 1024.0f), hann[n]));
     }
   }
-  float v = env > 1e-11f ? acc / env : acc;
-  v = fminf(fmaxf(v * pcm_scale, -32768.f), 32767.f);
-  pcm[n] = (int16_t)v;   // float -> int conversion truncates toward zero, as numpy astype does
+  __syncthreads();
+  int16_t* out = pcm + pcm_off[chunk] + (int64_t)h0 * 256;
+  for (int i = tid; i < hops * 256; i += 256) {
+    const int p = base + i;
+    const int fh = p >> 8;
+    float env = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int f = fh - d;
+      if (f >= 0 && f < n_frames) {
+        const float w = hann[p - f * 256];
+        env += w * w;
+      }
+    }
+    const float a = acc[i];
+    float v = env > 1e-11f ? a / env : a;
+    v = fminf(fmaxf(v * pcm_scale, -32768.f), 32767.f);
+    out[i] = (int16_t)v;   // float -> int conversion truncates toward zero, as numpy astype does
+  }
 }
 
-void launch_istft(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip, int n_frames,
-                  float* frames, float pcm_scale, int16_t* pcm, int64_t n_out, cudaStream_t st) {
-  if (n_frames <= 0) return;
-  istft_frames_kernel<<<n_frames, 256, 0, st>>>(head, ld_head, hann, tw, mag_clip, frames);
-  if (n_out > 0) ola_pcm_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(frames, hann, n_frames, pcm_scale, pcm, n_out);
+void launch_istft_ola(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip,
+                      const int32_t* dec_off, const int32_t* dec_len, const int64_t* pcm_off, int n_chunks,
+                      int max_frames, float pcm_scale, int16_t* pcm, cudaStream_t st) {
+  if (n_chunks <= 0 || max_frames <= 1) return;
+  dim3 grid((max_frames - 1 + OLA_HOPS - 1) / OLA_HOPS, n_chunks);
+  istft_ola_kernel<<<grid, 256, 0, st>>>(head, ld_head, hann, tw, mag_clip, dec_off, dec_len, pcm_off, pcm_scale, pcm);
 }
 
 // ------------------------------------------------------------------------------------------------ weight layout

@@ -20,8 +20,11 @@ void launch_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t key, cu
 void launch_noise_to_bf16(const float* noise, int rows_u, int n_mel, bf16* nb0, bf16* nb1, int ld, cudaStream_t st);
 void launch_voc_im2col(const float* mel, const int32_t* src_row, const int32_t* row_pos, const int32_t* row_len,
                        int rows, int n_mel, int K, int ld, bf16* out, cudaStream_t st);
-void launch_istft(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip, int n_frames,
-                  float* frames, float pcm_scale, int16_t* pcm, int64_t n_out, cudaStream_t st);
+// all chunks of a batch in one launch: chunk c owns head rows [dec_off[c], dec_off[c] + dec_len[c]) and writes
+// (dec_len[c] - 1) * 256 samples at pcm + pcm_off[c]; max_frames = max over dec_len (host copy)
+void launch_istft_ola(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip,
+                      const int32_t* dec_off, const int32_t* dec_len, const int64_t* pcm_off, int n_chunks,
+                      int max_frames, float pcm_scale, int16_t* pcm, cudaStream_t st);
 void launch_permute_conv_w(const float* w, int dim, int cg, int taps, bf16* out, cudaStream_t st);
 void launch_permute_embed_w(const float* w, int vd, int n_mel, int K, int ld, bf16* out, cudaStream_t st);
 

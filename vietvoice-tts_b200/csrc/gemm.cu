@@ -267,11 +267,8 @@ template <int BN, bool CONV>
 static void launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
                      int num_sms, cudaStream_t st) {
   using C = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gemm_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    attr_set = true;
-  }
+  static DeviceOnce attr;
+  attr.once([] { cudaFuncSetAttribute(gemm_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); });
   const int m_tiles = (s.M + BM - 1) / BM;
   const int n_tiles = CONV ? s.conv_groups : (s.N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;

@@ -390,12 +390,11 @@ void plan_pair_tail(int total, int clusters, int* full, int* split) {
 void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBt, const GemmShape& s,
                       const GemmEpi& e, int num_sms, cudaStream_t st) {
   using namespace pair;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr;
+  attr.once([] {
     cudaFuncSetAttribute(gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM);
     cudaFuncSetAttribute(gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM);
-    attr_set = true;
-  }
+  });
   const int m2_tiles = (s.M + 2 * BM - 1) / (2 * BM);
   const int total = m2_tiles * (s.N / BN);
   int clusters = num_sms / 2;

@@ -5,7 +5,31 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include <mutex>
+
 namespace vv {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting of a kernel: a process that creates engines
+// on several GPUs (the C ABI allows it) must set it once on each of them, and two threads may launch at the same time.
+// `once(fn)` runs fn the first time it is called with a given device current, under a mutex.
+class DeviceOnce {
+ public:
+  template <typename F>
+  void once(F&& fn) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    std::lock_guard<std::mutex> g(mu_);
+    if (!done_[dev]) {
+      fn();
+      done_[dev] = true;
+    }
+  }
+
+ private:
+  static constexpr int kMaxDevices = 64;
+  std::mutex mu_;
+  bool done_[kMaxDevices] = {};
+};
 
 typedef __nv_bfloat16 bf16;
 

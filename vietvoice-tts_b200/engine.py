@@ -95,18 +95,45 @@ class Engine:
     def batch(self, total_frames: Sequence[int]) -> "Batch":
         return Batch(self, total_frames)
 
+    # -- device-resident prompts -------------------------------------------------
+    def prompt_put(self, audio: np.ndarray) -> int:
+        """Make a prompt resident in HBM (PCM + log-mel + ref_signal_len) and return its content id.  A prompt that
+        is already resident is not uploaded again."""
+        a = np.ascontiguousarray(np.asarray(audio).reshape(-1), dtype=np.int16)
+        pid = C.c_uint64(0)
+        _lib.check(self.lib.vv_prompt_put(self._h, _ptr(a), a.size, C.byref(pid), None))
+        return int(pid.value)
+
+    def prompt_drop(self, prompt_id: int) -> None:
+        _lib.check(self.lib.vv_prompt_drop(self._h, int(prompt_id)))
+
+    def prompt_cache_clear(self) -> None:
+        _lib.check(self.lib.vv_prompt_cache_clear(self._h))
+
+    def prompt_cache_stats(self) -> Dict[str, int]:
+        w = (C.c_int64 * 3)()
+        _lib.check(self.lib.vv_prompt_cache_stats(self._h, w))
+        return {"resident": int(w[0]), "uploads": int(w[1]), "hits": int(w[2])}
+
     # -- whole path, host buffers ------------------------------------------------------------------
     def synthesize_batch(self, audios: Sequence[np.ndarray], text_ids: Sequence[np.ndarray],
                          total_frames: Sequence[int], noises: Optional[Sequence[Optional[np.ndarray]]] = None,
                          nfe: int = 0, seed: int = 9527, chunk_keys: Optional[Sequence[int]] = None,
-                         pcm_out: Optional[Sequence[np.ndarray]] = None) -> List[np.ndarray]:
-        """One call = preprocess -> (nfe-1) steps -> decode for B chunks; host arrays in, int16 PCM out."""
+                         pcm_out: Optional[Sequence[np.ndarray]] = None,
+                         prompt_ids: Optional[Sequence[int]] = None) -> List[np.ndarray]:
+        """One call = preprocess -> (nfe-1) steps -> decode for B chunks; host arrays in, int16 PCM out.
+        `prompt_ids[i]` (from `prompt_put`) names a resident prompt; without it the engine finds the prompt by hashing
+        audios[i] — chunks that pass the SAME array object are hashed once."""
         B = len(audios)
         reqs = (_lib.VVRequest * B)()
         keep = []
         outs = []
+        seen: Dict[int, np.ndarray] = {}
         for i in range(B):
-            a = np.ascontiguousarray(np.asarray(audios[i]).reshape(-1), dtype=np.int16)
+            a = seen.get(id(audios[i]))
+            if a is None:
+                a = np.ascontiguousarray(np.asarray(audios[i]).reshape(-1), dtype=np.int16)
+                seen[id(audios[i])] = a
             t = np.ascontiguousarray(np.asarray(text_ids[i]).reshape(-1), dtype=np.int32)
             T = int(total_frames[i])
             ref_len = a.size // self.arch.hop + 1
@@ -125,6 +152,7 @@ class Engine:
             reqs[i].chunk_key = int(chunk_keys[i]) if chunk_keys is not None else i
             reqs[i].pcm_out = o.ctypes.data
             reqs[i].pcm_capacity = o.size
+            reqs[i].prompt_id = int(prompt_ids[i]) if prompt_ids is not None and prompt_ids[i] else 0
             outs.append(o)
         _lib.check(self.lib.vv_synthesize_batch(self._h, reqs, B, nfe, seed))
         return [outs[i][: int(reqs[i].n_out)] for i in range(B)]
@@ -165,6 +193,19 @@ class Batch:
         self.ref_len[idx] = int(rl.value)
         return self.ref_len[idx]
 
+    def preprocess_prompt(self, idx: int, prompt_id: int, text_ids: np.ndarray, noise: Optional[np.ndarray] = None,
+                          seed: int = 9527, chunk_key: int = 0) -> int:
+        """`preprocess` for a prompt that is already resident (Engine.prompt_put): nothing but the ids is uploaded."""
+        t = np.ascontiguousarray(np.asarray(text_ids).reshape(-1), dtype=np.int32)
+        nz = None
+        if noise is not None:
+            nz = np.ascontiguousarray(noise, dtype=np.float32).reshape(self.T[idx], self.e.arch.n_mel)
+        rl = C.c_int64(0)
+        _lib.check(self.lib.vv_preprocess_prompt(self._h, idx, int(prompt_id), _ptr(t), t.size, _ptr(nz), seed,
+                                                 chunk_key, C.byref(rl)))
+        self.ref_len[idx] = int(rl.value)
+        return self.ref_len[idx]
+
     def sample(self, nfe: int = 0, first_step: int = 0, n_steps: Optional[int] = None) -> None:
         n = (nfe or self.e.arch.nfe) - 1 - first_step if n_steps is None else n_steps
         _lib.check(self.lib.vv_sample(self._h, nfe, first_step, n))
@@ -177,6 +218,12 @@ class Batch:
         ms = (C.c_float * 8)()
         _lib.check(self.lib.vv_profile_step(self._h, nfe, step, ms))
         return [float(x) for x in ms]
+
+    def profile_stages(self, nfe: int = 0) -> Dict[str, float]:
+        """resident path with events at the stage boundaries -> milliseconds per stage"""
+        ms = (C.c_float * 4)()
+        _lib.check(self.lib.vv_profile_stages(self._h, nfe, ms))
+        return {"pre_ms": float(ms[0]), "loop_ms": float(ms[1]), "decode_ms": float(ms[2]), "total_ms": float(ms[3])}
 
     def debug_partial_step(self, step: int, n_layers: int, nfe: int = 0) -> None:
         _lib.check(self.lib.vv_debug_partial_step(self._h, nfe, step, n_layers))
