@@ -110,3 +110,40 @@ def test_submit_is_thread_safe():
         [t.join() for t in ts]
     assert len(out) == 16 and all(v[0].shape == (8,) for v in out.values())
     assert tts.model_session_manager.engine.calls and sch.chunks_run == 32
+
+
+def test_worker_survives_cancels_engine_errors_and_close():
+    """a cancelled future made set_result raise InvalidStateError inside the worker, which killed the
+    daemon thread and left every later request hanging; requests queued behind close()'s sentinel never resolved;
+    a client-supplied nfe had no upper bound."""
+    import time
+
+    class _SlowEngine(_FakeEngine):
+        def synthesize_batch(self, *a, **k):
+            if k.get("nfe") == 17:
+                raise RuntimeError("device fell over")
+            time.sleep(0.05)
+            return super().synthesize_batch(*a, **k)
+
+    tts = _FakeTTS()
+    tts.model_session_manager.engine = _SlowEngine()
+    sch = RequestScheduler(tts, max_wait_s=0.01)
+    first = sch.submit("0:1")
+    queued = [sch.submit(f"{i}:1") for i in range(1, 6)]
+    cancelled = [f for f in queued if f.cancel()]               # still queued behind the slow first batch
+    assert first.result(timeout=10)[0].shape == (4,)
+    for f in queued:
+        if f not in cancelled:
+            assert f.result(timeout=10)[0].shape == (4,)
+    boom = sch.submit("6:2", nfe=17)                            # engine error: wrapped, the worker carries on
+    with pytest.raises(RuntimeError, match="Speech synthesis failed: device fell over"):
+        boom.result(timeout=10)
+    assert sch.submit("7:1").result(timeout=10)[0].shape == (4,)   # the worker is still alive
+    assert sch._worker.is_alive()
+    for bad in (1, 101, 100000):
+        with pytest.raises(ValueError, match="nfe must be between 2 and 100"):
+            sch.submit("8:1", nfe=bad).result(timeout=10)
+    sch.close()
+    assert not sch._worker.is_alive()
+    with pytest.raises(RuntimeError, match="scheduler is closed"):
+        sch.submit("9:1").result(timeout=10)                     # resolved at once instead of queueing forever

@@ -23,6 +23,11 @@ def test_assign_is_a_partition_and_balanced():
         assert max(loads) / (sum(loads) / world) < 1.08                  # greedy LPT stays within a few %
         assert parts == assign_chunks(frames, world)                      # deterministic
     assert assign_chunks([], 4) == [[], [], [], []]
+    # the cost model is read from the architecture, not hard-coded for dim 1024 / 22 layers
+    from vietvoice_tts_b200.arch import FULL, TINY
+    assert chunk_cost(1000) == chunk_cost(1000, FULL) == 1000 * (22 * 16 * 1024 ** 2 + 22 * 4 * 1024 * 1000)
+    assert chunk_cost(1000, TINY) == 1000 * (TINY.depth * (8 * TINY.dim ** 2 + 4 * TINY.dim * TINY.ff_dim)
+                                             + TINY.depth * 4 * TINY.dim * 1000)
     assert assign_chunks([1000], 2) == [[0], []]
 
 
@@ -39,6 +44,13 @@ def _worker(rank, world, port, q):
         ok = sorted(allw) == list(range(len(frames))) and all(
             allw[i].dtype == np.int16 and allw[i].shape[-1] == (frames[i] - 564) * 256 and int(allw[i][0, 0, 0]) == i
             for i in range(len(frames)))
+        # a rank whose synthesis failed still joins the collective: the error surfaces on EVERY rank at once
+        # instead of leaving the healthy ranks blocked in all_gather_object until the gloo timeout
+        try:
+            sh.gather({} if rank == 1 else local, len(frames), error="out of memory" if rank == 1 else None)
+            ok = False
+        except RuntimeError as exc:
+            ok = ok and "rank 1: out of memory" in str(exc)
         q.put((rank, mine, ok))
     finally:
         dist.destroy_process_group()

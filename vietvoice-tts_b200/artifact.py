@@ -225,9 +225,11 @@ def _wav_bytes(pcm: np.ndarray, sr: int) -> bytes:
 
 
 def build_model_tar(path: str, arch: ArchConfig, seed: int = 9527,
-                    voices: Iterable[dict] | None = None, prompt_seconds: float = 6.0) -> None:
-    """Write a tar with the member names core/model.py:73-77,84,109,207 expects."""
-    W = make_random_weights(arch, seed)
+                    voices: Iterable[dict] | None = None, prompt_seconds: float = 6.0,
+                    weights: Dict[str, np.ndarray] | None = None) -> None:
+    """Write a tar with the member names core/model.py:73-77,84,109,207 expects.  `weights`: reuse an already
+    generated `make_random_weights(arch, seed)` dict instead of drawing it again."""
+    W = weights if weights is not None else make_random_weights(arch, seed)
     if voices is None:
         voices = [
             {"gender": "female", "group": "audiobook", "area": "northern", "emotion": "neutral"},

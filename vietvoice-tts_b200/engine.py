@@ -129,11 +129,19 @@ class Engine:
         keep = []
         outs = []
         seen: Dict[int, np.ndarray] = {}
+        shared: Dict[int, int] = {}
         for i in range(B):
             a = seen.get(id(audios[i]))
             if a is None:
                 a = np.ascontiguousarray(np.asarray(audios[i]).reshape(-1), dtype=np.int16)
                 seen[id(audios[i])] = a
+            elif prompt_ids is None and id(audios[i]) not in shared:
+                # the same array object again (chunks of one text share their prompt): make it resident once and
+                # hand its id to every chunk instead of having each request's audio hashed
+                try:
+                    shared[id(audios[i])] = self.prompt_put(a)
+                except _lib.VVError:
+                    shared[id(audios[i])] = 0          # prompt cache disabled: the plain path uploads per chunk
             t = np.ascontiguousarray(np.asarray(text_ids[i]).reshape(-1), dtype=np.int32)
             T = int(total_frames[i])
             ref_len = a.size // self.arch.hop + 1
@@ -152,7 +160,10 @@ class Engine:
             reqs[i].chunk_key = int(chunk_keys[i]) if chunk_keys is not None else i
             reqs[i].pcm_out = o.ctypes.data
             reqs[i].pcm_capacity = o.size
-            reqs[i].prompt_id = int(prompt_ids[i]) if prompt_ids is not None and prompt_ids[i] else 0
+            if prompt_ids is not None:
+                reqs[i].prompt_id = int(prompt_ids[i] or 0)
+            else:
+                reqs[i].prompt_id = shared.get(id(audios[i]), 0)
             outs.append(o)
         _lib.check(self.lib.vv_synthesize_batch(self._h, reqs, B, nfe, seed))
         return [outs[i][: int(reqs[i].n_out)] for i in range(B)]

@@ -55,6 +55,21 @@ class _Request:
     waves: Dict[int, np.ndarray] = field(default_factory=dict)
 
 
+MAX_NFE = 100      # upper bound of ModelConfig.nfe_step (/root/reference/vietvoicetts/core/model_config.py:59-62)
+
+
+def _resolve(fut: Future, result=None, error: Optional[BaseException] = None) -> None:
+    """set_result / set_exception that tolerates a future the client cancelled or that is already resolved (an
+    InvalidStateError here used to kill the worker thread and leave every later request hanging)"""
+    try:
+        if error is not None:
+            fut.set_exception(error)
+        else:
+            fut.set_result(result)
+    except Exception:
+        pass
+
+
 def plan_batches(frames: Sequence[int], max_chunks: int, max_frames: int) -> List[List[int]]:
     """Greedy longest-first packing of chunk indices into micro-batches: a batch closes when it holds `max_chunks`
     chunks or the next chunk would push it over `max_frames` mel frames.  Every index appears exactly once; a chunk
@@ -85,6 +100,7 @@ class RequestScheduler:
         self.max_wait_s = max_wait_s
         self.rank, self.world = rank, world
         self._q: "queue.Queue[Optional[_Request]]" = queue.Queue()
+        self._closed = False
         self._next_id = 0
         self._id_lock = threading.Lock()
         self.batches_run = 0
@@ -109,11 +125,16 @@ class RequestScheduler:
         if not self.owns(rid):
             fut.set_result(None)
             return fut
-        if nfe is not None and nfe < 2:
-            fut.set_exception(ValueError("nfe must be >= 2"))
+        if nfe is not None and not (2 <= int(nfe) <= MAX_NFE):
+            # ModelConfig caps nfe_step at 100 (model_config.py:59-62); a per-request value must not bypass that: every
+            # distinct nfe costs a modulation table and a captured graph per cached batch on the device
+            fut.set_exception(ValueError(f"nfe must be between 2 and {MAX_NFE}, got {nfe}"))
             return fut
         if speed is not None and not (0.1 <= speed <= 5.0):      # same range as ModelConfig.__post_init__
             fut.set_exception(ValueError(f"speed must be between 0.1 and 5.0, got {speed}"))
+            return fut
+        if self._closed or not self._worker.is_alive():
+            fut.set_exception(RuntimeError("Speech synthesis failed: the request scheduler is closed"))
             return fut
         voice = dict(gender=gender, group=group, area=area, emotion=emotion, sample_iteration=sample_iteration,
                      reference_audio=reference_audio, reference_text=reference_text)
@@ -122,6 +143,7 @@ class RequestScheduler:
         return fut
 
     def close(self) -> None:
+        self._closed = True
         self._q.put(None)
         self._worker.join(timeout=60)
 
@@ -165,35 +187,50 @@ class RequestScheduler:
         eng = self.tts.model_session_manager.engine
         while True:
             reqs, stop = self._drain()
-            by_nfe: Dict[int, List[_Chunk]] = {}
-            for r in reqs:
-                try:
-                    for c in self._chunks_of(r):
-                        by_nfe.setdefault(r.nfe, []).append(c)
-                except Exception as exc:                      # same wrapping as TTSEngine.synthesize
-                    r.future.set_exception(RuntimeError(f"Speech synthesis failed: {exc}"))
-            for nfe, chunks in sorted(by_nfe.items()):
-                # one engine call per (micro-batch, seed): the seed is an argument of the batch call
-                for seed in sorted({c.req.seed for c in chunks}):
-                    group = [c for c in chunks if c.req.seed == seed]
-                    for batch in plan_batches([c.frames for c in group], self.max_batch_chunks, self.max_batch_frames):
-                        sel = [group[i] for i in batch]
-                        try:
-                            out = eng.synthesize_batch([c.audio for c in sel], [c.ids for c in sel],
-                                                       [c.frames for c in sel], nfe=nfe, seed=seed,
-                                                       chunk_keys=[c.index for c in sel])
-                        except Exception as exc:
-                            for c in sel:
-                                if not c.req.future.done():
-                                    c.req.future.set_exception(RuntimeError(f"Speech synthesis failed: {exc}"))
-                            continue
-                        self.batches_run += 1
-                        self.chunks_run += len(sel)
-                        for c, w in zip(sel, out):
-                            c.req.waves[c.index] = np.array(w, copy=True).reshape(1, 1, -1)
-                            self._finish(c.req, cfg)
+            # a request the client cancelled while it was queued is skipped; the others are RUNNING from here on
+            reqs = [r for r in reqs if r.future.set_running_or_notify_cancel()]
+            try:
+                self._serve(reqs, cfg, eng)
+            except BaseException as exc:              # nothing may take the worker down with requests in flight
+                for r in reqs:
+                    _resolve(r.future, error=RuntimeError(f"Speech synthesis failed: {exc}"))
             if stop:
+                break
+        while True:                                   # whatever was queued behind the stop sentinel
+            try:
+                r = self._q.get_nowait()
+            except queue.Empty:
                 return
+            if r is not None and r.future.set_running_or_notify_cancel():
+                _resolve(r.future, error=RuntimeError("Speech synthesis failed: the request scheduler is closed"))
+
+    def _serve(self, reqs: List[_Request], cfg, eng) -> None:
+        by_nfe: Dict[int, List[_Chunk]] = {}
+        for r in reqs:
+            try:
+                for c in self._chunks_of(r):
+                    by_nfe.setdefault(r.nfe, []).append(c)
+            except Exception as exc:                      # same wrapping as TTSEngine.synthesize
+                _resolve(r.future, error=RuntimeError(f"Speech synthesis failed: {exc}"))
+        for nfe, chunks in sorted(by_nfe.items()):
+            # one engine call per (micro-batch, seed): the seed is an argument of the batch call
+            for seed in sorted({c.req.seed for c in chunks}):
+                group = [c for c in chunks if c.req.seed == seed]
+                for batch in plan_batches([c.frames for c in group], self.max_batch_chunks, self.max_batch_frames):
+                    sel = [group[i] for i in batch]
+                    try:
+                        out = eng.synthesize_batch([c.audio for c in sel], [c.ids for c in sel],
+                                                   [c.frames for c in sel], nfe=nfe, seed=seed,
+                                                   chunk_keys=[c.index for c in sel])
+                    except Exception as exc:
+                        for c in sel:
+                            _resolve(c.req.future, error=RuntimeError(f"Speech synthesis failed: {exc}"))
+                        continue
+                    self.batches_run += 1
+                    self.chunks_run += len(sel)
+                    for c, w in zip(sel, out):
+                        c.req.waves[c.index] = np.array(w, copy=True).reshape(1, 1, -1)
+                        self._finish(c.req, cfg)
 
     def _finish(self, r: _Request, cfg) -> None:
         if r.future.done() or len(r.waves) < r.n_chunks:
@@ -201,6 +238,6 @@ class RequestScheduler:
         try:
             final = self.tts.audio_processor.concatenate_with_crossfade_improved(
                 [r.waves[i] for i in range(r.n_chunks)], cfg.cross_fade_duration, cfg.sample_rate)
-            r.future.set_result((final, time.time() - r.t0))
+            _resolve(r.future, (final, time.time() - r.t0))
         except Exception as exc:
-            r.future.set_exception(RuntimeError(f"Speech synthesis failed: {exc}"))
+            _resolve(r.future, error=RuntimeError(f"Speech synthesis failed: {exc}"))

@@ -38,6 +38,7 @@ class TTSEngine:
         self.sample_cache = {}
         self.use_sessions = use_sessions
         self.shard = shard               # optional vietvoice_tts_b200.shard.Sharder
+        self.last_timing: dict = {}      # seconds per stage of the last synthesize() call (bench / logging only)
 
     def cleanup(self) -> None:
         if self.model_session_manager:
@@ -137,15 +138,25 @@ class TTSEngine:
     def _synthesize_chunks_batched(self, inputs_list) -> List[np.ndarray]:
         eng = self.model_session_manager.engine
         n = len(inputs_list)
-        mine = list(range(n)) if self.shard is None else self.shard.assign([int(i[2][0]) for i in inputs_list])
-        local = {}
-        if mine:
-            out = eng.synthesize_batch([inputs_list[i][0] for i in mine], [inputs_list[i][1] for i in mine],
-                                       [int(inputs_list[i][2][0]) for i in mine], nfe=self.config.nfe_step,
-                                       seed=self.config.random_seed, chunk_keys=mine)
-            local = {i: w.reshape(1, 1, -1) for i, w in zip(mine, out)}
         if self.shard is not None:
-            local = self.shard.gather(local, n)
+            self.shard.arch = eng.arch                       # chunk costs from the loaded architecture
+        mine = list(range(n)) if self.shard is None else self.shard.assign([int(i[2][0]) for i in inputs_list])
+        local, failure = {}, None
+        t0 = time.time()
+        if mine:
+            try:
+                out = eng.synthesize_batch([inputs_list[i][0] for i in mine], [inputs_list[i][1] for i in mine],
+                                           [int(inputs_list[i][2][0]) for i in mine], nfe=self.config.nfe_step,
+                                           seed=self.config.random_seed, chunk_keys=mine)
+                local = {i: w.reshape(1, 1, -1) for i, w in zip(mine, out)}
+            except Exception as exc:
+                if self.shard is None:
+                    raise
+                failure = exc            # still take part in the gather: the other ranks are waiting in it
+        t1 = time.time()
+        if self.shard is not None:
+            local = self.shard.gather(local, n, error=None if failure is None else str(failure))
+        self.last_timing.update(synth_s=t1 - t0, gather_s=time.time() - t1, n_chunks=n, local_chunks=len(mine))
         return [local[i] for i in range(n)]
 
     def synthesize(self, text: str, gender: Optional[str] = None, group: Optional[str] = None,
@@ -157,14 +168,18 @@ class TTSEngine:
         ref_audio, ref_text = self.model_session_manager.select_sample(
             gender, group, area, emotion, sample_iteration, reference_audio, reference_text)
         try:
+            self.last_timing = {}
             inputs_list = self._prepare_inputs(ref_audio, ref_text, text)
+            t1 = time.time()
             if self.use_sessions or self.config.fuse_nfe != 1:
                 waves = self._synthesize_chunks_sessions(inputs_list)
             else:
                 waves = self._synthesize_chunks_batched(inputs_list)
+            t2 = time.time()
             final = self.audio_processor.concatenate_with_crossfade_improved(
                 waves, self.config.cross_fade_duration, self.config.sample_rate)
             elapsed = time.time() - t0
+            self.last_timing.update(prepare_s=t1 - t0, crossfade_s=time.time() - t2, total_s=elapsed)
             if output_path:
                 self.audio_processor.save_audio(final, output_path, self.config.sample_rate)
                 logger.info(f"Audio saved to: {output_path}")

@@ -12,31 +12,43 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-# algorithmic FLOPs per token of one DiT forward: 22 x (16 d^2 + 4 T d) at d = 1024
-_LIN = 22 * 16 * 1024 * 1024
-_ATT = 22 * 4 * 1024
+from .arch import FULL, ArchConfig
 
 
-def chunk_cost(total_frames: int) -> float:
+def chunk_cost(total_frames: int, arch: ArchConfig = FULL) -> float:
+    """Algorithmic FLOPs of one DiT forward over `total_frames` tokens: depth x (linear layers + attention), read from
+    the architecture (per token per layer 6 d^2 (QKV) + 2 d^2 (out) + 4 d ff (FFN) + 4 T d (attention))."""
     t = float(total_frames)
-    return t * (_LIN + _ATT * t)
+    d, ff = arch.dim, arch.ff_dim
+    lin = arch.depth * (8 * d * d + 4 * d * ff)
+    att = arch.depth * 4 * d
+    return t * (lin + att * t)
 
 
-def assign_chunks(total_frames: Sequence[int], world: int) -> List[List[int]]:
+def assign_chunks(total_frames: Sequence[int], world: int, arch: ArchConfig = FULL) -> List[List[int]]:
     """-> per-rank list of chunk indices (ascending).  Deterministic: ties broken by index, then by rank."""
-    order = sorted(range(len(total_frames)), key=lambda i: (-chunk_cost(total_frames[i]), i))
+    order = sorted(range(len(total_frames)), key=lambda i: (-chunk_cost(total_frames[i], arch), i))
     load = [0.0] * world
     out: List[List[int]] = [[] for _ in range(world)]
     for i in order:
         r = min(range(world), key=lambda k: (load[k], k))
         out[r].append(i)
-        load[r] += chunk_cost(total_frames[i])
+        load[r] += chunk_cost(total_frames[i], arch)
     return [sorted(x) for x in out]
 
 
+def imbalance(total_frames: Sequence[int], world: int, arch: ArchConfig = FULL) -> float:
+    """max over ranks of the assigned cost / mean cost (1.0 = perfectly balanced): the LPT part of a strong-scaling
+    loss, before any GPU effect."""
+    parts = assign_chunks(total_frames, world, arch)
+    loads = [sum(chunk_cost(total_frames[i], arch) for i in p) for p in parts]
+    mean = sum(loads) / max(world, 1)
+    return max(loads) / mean if mean > 0 else 1.0
+
+
 class Sharder:
-    def __init__(self, rank: int = 0, world: int = 1, group=None):
-        self.rank, self.world, self.group = rank, world, group
+    def __init__(self, rank: int = 0, world: int = 1, group=None, arch: ArchConfig = FULL):
+        self.rank, self.world, self.group, self.arch = rank, world, group, arch
 
     @classmethod
     def from_torch_distributed(cls) -> "Sharder":
@@ -49,15 +61,25 @@ class Sharder:
         return cls(dist.get_rank(), dist.get_world_size(), group)
 
     def assign(self, total_frames: Sequence[int]) -> List[int]:
-        return assign_chunks(total_frames, self.world)[self.rank]
+        return assign_chunks(total_frames, self.world, self.arch)[self.rank]
 
-    def gather(self, local: Dict[int, np.ndarray], n_chunks: int) -> Dict[int, np.ndarray]:
-        """All ranks receive every chunk's waveform, keyed by chunk index."""
+    def gather(self, local: Dict[int, np.ndarray], n_chunks: int, error: Optional[str] = None) -> Dict[int, np.ndarray]:
+        """All ranks receive every chunk's waveform, keyed by chunk index.  A rank whose synthesis failed still takes
+        part, passing `error`: the failure is then raised on EVERY rank instead of leaving the others blocked in the
+        collective until its timeout."""
         if self.world == 1:
+            if error is not None:
+                raise RuntimeError(error)
             return dict(local)
         import torch.distributed as dist
         parts: List[Optional[dict]] = [None] * self.world
-        dist.all_gather_object(parts, {int(k): np.asarray(v) for k, v in local.items()}, group=self.group)
+        mine: dict = {int(k): np.asarray(v) for k, v in local.items()}
+        if error is not None:
+            mine = {"__error__": f"rank {self.rank}: {error}"}
+        dist.all_gather_object(parts, mine, group=self.group)
+        failed = [p["__error__"] for p in parts if p and "__error__" in p]
+        if failed:
+            raise RuntimeError("; ".join(failed))
         merged: Dict[int, np.ndarray] = {}
         for p in parts:
             merged.update(p or {})
