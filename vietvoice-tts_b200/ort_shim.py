@@ -252,6 +252,11 @@ class InferenceSession:
         return [b.decode(0).reshape(1, 1, -1)]
 
 
-def install() -> None:
-    """Make `import onnxruntime` resolve to this module (for running the reference's Python unmodified)."""
+def install(audio: bool = True) -> None:
+    """Make `import onnxruntime` resolve to this module (for running the reference's Python unmodified).  With
+    `audio`, `pydub` and `soundfile` — imported by the reference at module load, absent on offline hosts — get
+    WAV-only stand-ins (audio_shims.py) unless the real packages are importable."""
     sys.modules["onnxruntime"] = sys.modules[__name__]
+    if audio:
+        from . import audio_shims
+        audio_shims.install()
