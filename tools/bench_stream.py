@@ -76,7 +76,8 @@ def run_stream(tts, reqs, rank=0, world=1, max_batch_chunks=8, max_batch_frames=
                 time.sleep(delay)
             t0 = time.time()
             try:
-                res = sch.submit(text, gender=v["gender"], area=v["area"], emotion=v["emotion"], nfe=nfe).result(600)
+                res = sch.submit(text, gender=v["gender"], group=v["group"], area=v["area"], emotion=v["emotion"],
+                                 nfe=nfe).result(600)
             except Exception as ex:
                 with lock:
                     errs.append(repr(ex))
