@@ -272,7 +272,9 @@ __device__ __forceinline__ void softmax_role(const AttnParams& p, uint32_t tmem_
             tc_fence_after();
           }
           T2(4);   // wait PV(j-1)
-          if (ASSIST >= 32) tmem_st16(tp + MAIN / 2, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+#pragma unroll
+          for (int g = 0; g < ASSIST / 32; ++g)
+            tmem_st16(tp + MAIN / 2 + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[g * 16]));
           if (ASSIST % 32) tmem_st8(tp + MAIN / 2 + (ASSIST / 32) * 16, *reinterpret_cast<uint32_t(*)[8]>(&pk[(ASSIST / 32) * 16]));
           const float sum = (sa0 + sa1) + (sb0 + sb1);
           bad |= !(sum < SUM_LIMIT);

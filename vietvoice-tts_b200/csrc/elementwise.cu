@@ -98,87 +98,6 @@ void launch_ln_mod(const float* x, int rows, int dim, const float* shift, const 
                    cudaStream_t st) {
   launch_ln_any<false>(x, rows, dim, shift, scale, eps, out, nullptr, st);
 }
-
-// ---------------------------------------------------------------------------------- LayerNorm overlapped with its producer
-// LN-modulate of the rows a CTA-pair reduce-add GEMM (gemm2.cu) is still producing.  The GEMM is tensor-bound and
-// persistent (one CTA per SM, a third of the register file); this kernel is HBM/L2-bound, needs no shared memory and
-// fits beside it: launched with programmatic dependent launch it becomes resident while the GEMM runs, and each CTA
-// (8 rows, ascending — the order the GEMM finishes row blocks in) waits for the ready counter of its 256-row block.
-// x is then read out of L2 right after the reduce-add put it there instead of being fetched from HBM a kernel later,
-// and the 1.2 ms per DiT evaluation the stand-alone pass cost runs under the GEMMs.
-// Safe against deadlock: the dependent grid is launched only after EVERY CTA of the GEMM has started (they all fit:
-// grid <= SM count), so the producer never waits for a slot a spinning consumer holds.
-__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-template <int VEC4_PER_LANE>
-__global__ void __launch_bounds__(256)
-ln_dep_kernel(const float* __restrict__ x, int rows, int dim, const float* __restrict__ shift,
-              const float* __restrict__ scale, float eps, bf16* __restrict__ out, const int32_t* __restrict__ ready,
-              int epoch, ReadyPlan plan) {
-  pdl_trigger();
-  const int row0 = blockIdx.x * 8;
-  if (threadIdx.x == 0) {
-    const int m2 = row0 >> 8;                       // 8 divides 256: a CTA never straddles two row blocks
-    int inc = 0;
-    for (int n = 0; n < plan.n_tiles; ++n)
-      inc += (m2 * plan.n_tiles + n >= plan.full_tiles) ? plan.per_unit * plan.split : plan.per_unit;
-    const int target = inc * epoch;
-    while (ld_acquire_gpu(ready + m2) < target) __nanosleep(128);
-  }
-  __syncthreads();
-  const int row = row0 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * dim);
-  float4 v[VEC4_PER_LANE];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC4_PER_LANE; ++i) {
-    v[i] = __ldcg(xr + lane + 32 * i);              // L2 (where the reduce-add left it), never a stale L1 line
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-  }
-  const float mean = warp_sum(s) / dim;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC4_PER_LANE; ++i) {
-    float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-    q += dx * dx + dy * dy + dz * dz + dw * dw;
-  }
-  const float rstd = rsqrtf(warp_sum(q) / dim + eps);
-#pragma unroll
-  for (int i = 0; i < VEC4_PER_LANE; ++i) {
-    const int c4 = lane + 32 * i;
-    const float4 pa = __ldg(reinterpret_cast<const float4*>(shift) + c4);
-    const float4 pb = __ldg(reinterpret_cast<const float4*>(scale) + c4);
-    float4 y;
-    y.x = (v[i].x - mean) * rstd * (1.f + pb.x) + pa.x;
-    y.y = (v[i].y - mean) * rstd * (1.f + pb.y) + pa.y;
-    y.z = (v[i].z - mean) * rstd * (1.f + pb.z) + pa.z;
-    y.w = (v[i].w - mean) * rstd * (1.f + pb.w) + pa.w;
-    uint2 u;
-    u.x = pack_bf16(y.x, y.y);
-    u.y = pack_bf16(y.z, y.w);
-    reinterpret_cast<uint2*>(out + (size_t)row * dim)[c4] = u;
-  }
-}
-
-void launch_ln_mod_dep(const float* x, int rows, int dim, const float* shift, const float* scale, float eps, bf16* out,
-                       const int32_t* ready, int epoch, const ReadyPlan& plan, cudaStream_t st) {
-  const int grid = (rows + 7) / 8;
-  if (grid == 0) return;
-  switch (dim / 128) {
-    case 1: launch_k_dep(ln_dep_kernel<1>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    case 2: launch_k_dep(ln_dep_kernel<2>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    case 4: launch_k_dep(ln_dep_kernel<4>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    case 8: launch_k_dep(ln_dep_kernel<8>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    case 12: launch_k_dep(ln_dep_kernel<12>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    case 16: launch_k_dep(ln_dep_kernel<16>, grid, 256, 0, st, x, rows, dim, shift, scale, eps, out, ready, epoch, plan); break;
-    default: break;
-  }
-}
 void launch_ln_affine(const float* x, int rows, int dim, const float* g, const float* b, float eps, bf16* out_bf16,
                       float* out_f32, cudaStream_t st) {
   launch_ln_any<true>(x, rows, dim, g, b, eps, out_bf16, out_f32, st);

@@ -170,7 +170,6 @@ struct vv_batch {
   int32_t *tile_seq_d = nullptr, *tile_q0_d = nullptr;
   int n_tiles = 0;
   int32_t* ids_d = nullptr;
-  int32_t* ln_ready = nullptr;          // per 256-row block: reduce-add GEMM -> overlapped LayerNorm (run_step)
   int32_t* ids_h = nullptr;             // pinned staging for the id upload
   size_t ids_h_bytes = 0;
   float* noise0 = nullptr;              // y0 as preprocessed (restored by vv_run_resident)
@@ -783,7 +782,6 @@ extern "C" int vv_batch_create(vv_engine* e, int B, const int64_t* total_frames,
   UP(b->tile_seq_d, tile_seq);
   UP(b->tile_q0_d, tile_q0);
   AB(b->ids_d, M);
-  AB(b->ln_ready, M / 256 + 8);
   AB(b->noise0, (size_t)R * a.n_mel);
   {  // pinned staging buffer for the text ids: recycled through the engine (cudaMallocHost costs milliseconds)
     const size_t need = (size_t)R * 4;
@@ -1195,47 +1193,12 @@ struct PdlScope {
   ~PdlScope() { pdl_set(false); }
 };
 
-// VVB200_LN_OVERLAP=0: every LayerNorm-modulate runs as a stand-alone pass after its producer (A/B runs)
-// 1: after both residual GEMMs, 2: the GEMMs signal but every LN still runs stand-alone (cost of the signalling alone),
-// 3: after FFN-down only, 4: after out-proj only
-static int ln_overlap_mode() {
-  static const int mode = [] {
-    const char* v = getenv("VVB200_LN_OVERLAP");
-    return v ? atoi(v) : 1;
-  }();
-  return mode;
-}
-
 // one DiT evaluation (both CFG branches) + Euler update.  n_layers < 0: all layers + final projection.
 static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
   vv_engine* e = b->e;
   PdlScope pdl(want_pdl(b));
   const vv_arch& a = e->a;
   const int M = b->M, d = a.dim;
-  // The LayerNorm-modulate that follows a residual-update GEMM (out-proj -> LN2, FFN-down -> LN1 of the next block /
-  // the final LN) is launched as a programmatic dependent of that GEMM and follows it row block by row block
-  // (launch_ln_mod_dep): the bandwidth-bound pass runs under the tensor-bound one instead of after it.
-  const int ovl_mode = ln_overlap_mode();
-  const bool overlap = ovl_mode != 0;
-  int epoch = 0;                 // reduce-add GEMMs that have signalled on b->ln_ready since it was zeroed
-  bool signalled = false;        // the launch just before this point was such a GEMM
-  ReadyPlan plan;
-  if (overlap) CK(cudaMemsetAsync(b->ln_ready, 0, (size_t)(M / 256 + 8) * 4, e->st));
-  auto residual_gemm = [&](const GemmOp& op, GemmEpi& ep, bool is_ffn) {
-    signalled = overlap && op.bn == 512 && gemm_pair_signals_ready(op.s, ep, e->num_sms, &plan);
-    if (signalled) {
-      ep.ready = b->ln_ready;
-      ++epoch;
-    }
-    run_gemm(e, op, ep);
-    if (ovl_mode == 2 || (ovl_mode == 3 && !is_ffn) || (ovl_mode == 4 && is_ffn)) signalled = false;
-  };
-  auto ln_mod = [&](const float* shift, const float* scale) {
-    if (signalled) launch_ln_mod_dep(b->x, M, d, shift, scale, a.ln_eps, b->hb, b->ln_ready, epoch, plan, e->st);
-    else launch_ln_mod(b->x, M, d, shift, scale, a.ln_eps, b->hb, e->st);
-    signalled = false;
-    e->launches++;
-  };
   const float *c1b = nullptr, *c2b = nullptr, *outb = nullptr;
   TRY(need_w(e, "dit.pos.c1.b", &c1b, d));
   TRY(need_w(e, "dit.pos.c2.b", &c2b, d));
@@ -1258,7 +1221,8 @@ static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
   for (int l = 0; l < L; ++l) {
     const LayerW& W = e->layers[l];
     const float* m = mt.blocks + ((size_t)step * a.depth + l) * 6 * d;
-    ln_mod(m, m + d);
+    launch_ln_mod(b->x, M, d, m, m + d, a.ln_eps, b->hb, e->st);
+    e->launches++;
     GemmEpi eq;
     eq.bias = W.qkv_b; eq.out_bf16 = b->qkv; eq.ld_bf16 = 3 * d;
     eq.rope_dim = a.rope_heads * a.head_dim; eq.rope_off2 = d; eq.row_pos = b->row_pos_d; eq.rope_cs = e->rope_cs;
@@ -1266,18 +1230,20 @@ static int run_step(vv_batch* b, const ModTable& mt, int step, int n_layers) {
     run_attention(b);
     GemmEpi eo;
     eo.bias = W.out_b; eo.gate = m + 2 * d; eo.resid = b->x; eo.ld_resid = d; eo.out_f32 = b->x; eo.ld_f32 = d;
-    residual_gemm(b->op_out[l], eo, false);
-    ln_mod(m + 3 * d, m + 4 * d);
+    run_gemm(e, b->op_out[l], eo);
+    launch_ln_mod(b->x, M, d, m + 3 * d, m + 4 * d, a.ln_eps, b->hb, e->st);
+    e->launches++;
     GemmEpi e1;
     e1.bias = W.ff1_b; e1.act = ACT_GELU_TANH; e1.out_bf16 = b->ffb; e1.ld_bf16 = a.ff_dim;
     run_gemm(e, b->op_ff1[l], e1);
     GemmEpi e2;
     e2.bias = W.ff2_b; e2.gate = m + 5 * d; e2.resid = b->x; e2.ld_resid = d; e2.out_f32 = b->x; e2.ld_f32 = d;
-    residual_gemm(b->op_ff2[l], e2, true);
+    run_gemm(e, b->op_ff2[l], e2);
   }
   if (n_layers < 0) {
     const float* f = mt.fin + (size_t)step * 2 * d;  // (scale, shift)
-    ln_mod(f + d, f);
+    launch_ln_mod(b->x, M, d, f + d, f, a.ln_eps, b->hb, e->st);
+    e->launches++;
     GemmEpi ef;
     ef.bias = outb; ef.out_f32 = b->v; ef.ld_f32 = 128;
     run_gemm(e, b->op_fin, ef);

@@ -314,14 +314,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_commit();
           }
         }
-        if (e.ready != nullptr && lane == 0) {
-          // this warp's part of the unit is in x: tell the dependent LayerNorm (release at gpu scope after the bulk
-          // reduce-adds, which run in the async proxy, have completed)
-          tma_store_wait_all<0>();
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __threadfence();
-          atomicAdd(e.ready + un.m2, 1);
-        }
       } else {
 #pragma unroll 1
         for (int c = c0; c < c0 + ch_per; ++c) {
@@ -368,20 +360,6 @@ static bool reduce_epilogue_ok(const GemmEpi& e) {
   return e.resid && e.out_f32 == e.resid && e.ld_f32 == e.ld_resid && !e.out_bf16 && !e.row_mask &&
          e.rope_dim == 0 && e.act == ACT_NONE && (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 &&
          e.ld_f32 % 4 == 0;
-}
-
-bool gemm_pair_signals_ready(const GemmShape& s, const GemmEpi& e, int num_sms, ReadyPlan* plan) {
-  if (!gemm_pair_supported(s, e) || !reduce_epilogue_ok(e)) return false;
-  const int m2_tiles = (s.M + 2 * pair::BM - 1) / (2 * pair::BM);
-  const int total = m2_tiles * (s.N / pair::BN);
-  const int clusters = num_sms / 2;
-  if (clusters < 1 || total < 1) return false;
-  plan->n_tiles = s.N / pair::BN;
-  plan->full_tiles = total;
-  plan->split = 1;
-  plan_pair_tail(total, clusters, &plan->full_tiles, &plan->split);      // launch_gemm_pair always passes tmBt here
-  plan->per_unit = 2 * pair::EPI_WARPS;                                  // every epilogue warp of both CTAs, once per unit
-  return true;
 }
 
 // How to cut the tiles of the last, partial wave: the split (1, 2 or 4 column slices per tile) with the smallest

@@ -53,10 +53,6 @@ struct GemmEpi {
   int rope_dim = 0;                   // columns [0,rope_dim) and [rope_off2, rope_off2+rope_dim) are rotated
   int rope_off2 = 0;
   int act = ACT_NONE;
-  // CTA-pair reduce-add epilogue only (gemm_pair_signals_ready): one counter per 256-row block, incremented by every
-  // epilogue warp once its reduce-adds of a work unit are complete — a dependent LayerNorm launched with
-  // programmatic dependent launch starts on a row block as soon as the GEMM has finished it (launch_ln_mod_dep)
-  int32_t* ready = nullptr;
 };
 
 struct GemmShape {
@@ -90,23 +86,6 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// always with the programmatic-serialization attribute: the kernel may start while its predecessor in the stream is
-// still running and must synchronise with it by itself (griddepcontrol.wait, or finer-grained flags)
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-
 // 2-D bf16 tensor map, 128B swizzle, box = {64 columns, box_rows rows}
 CUtensorMap make_tmap_bf16(const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 
@@ -119,13 +98,6 @@ bool gemm_pair_supported(const GemmShape& s, const GemmEpi& e);
 void launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBt, const GemmShape& s,
                       const GemmEpi& e, int num_sms, cudaStream_t st);
 void plan_pair_tail(int total_tiles, int clusters, int* full_tiles, int* split);
-// true when launch_gemm_pair(s, e) takes the reduce-add epilogue that increments e.ready; fills the plan a dependent
-// kernel needs to know how many increments complete a 256-row block: every work unit (a 256-column tile, or one of the
-// `split` column slices of a tile >= full_tiles) adds `per_unit` to the counter of its row block
-struct ReadyPlan {
-  int n_tiles = 0, full_tiles = 0, split = 1, per_unit = 0;
-};
-bool gemm_pair_signals_ready(const GemmShape& s, const GemmEpi& e, int num_sms, ReadyPlan* plan);
 void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e, int bn,
                  int num_sms, cudaStream_t st, const CUtensorMap* tmBt = nullptr);
 
@@ -161,12 +133,6 @@ bool launch_attention_split(const CUtensorMap& tmQKV, const AttnParams& p, cudaS
 // If x2 != null computes the CFG-combined row:  (1+cfg)*h(x) - cfg*h(x2)   (used by nobody yet)
 void launch_ln_mod(const float* x, int rows, int dim, const float* shift, const float* scale, float eps, bf16* out,
                    cudaStream_t st);
-// The same, OVERLAPPED with the CTA-pair reduce-add GEMM that is still producing x (the kernel launched just before it
-// on `st` with GemmEpi::ready = `ready`): launched with programmatic dependent launch, each CTA (8 rows) waits until
-// the counter of its 256-row block has reached `epoch` x (increments per block, from `plan`), then normalises.
-// `epoch` = number of GEMMs that have signalled on `ready` since it was last zeroed, this one included.
-void launch_ln_mod_dep(const float* x, int rows, int dim, const float* shift, const float* scale, float eps, bf16* out,
-                       const int32_t* ready, int epoch, const ReadyPlan& plan, cudaStream_t st);
 // LayerNorm with affine (gamma,beta), fp32 in -> bf16 and/or fp32 out.
 void launch_ln_affine(const float* x, int rows, int dim, const float* g, const float* b, float eps, bf16* out_bf16,
                       float* out_f32, cudaStream_t st);
