@@ -17,6 +17,9 @@
  *       <- ModelSessionManager.select_sample re-reading the prompt WAV from the tar on every call
  *          (vietvoicetts/core/model.py:204-211) and TTSEngine's never-used sample_cache
  *          (vietvoicetts/core/tts_engine.py:30): prompt PCM, its log-mel and ref_signal_len stay in HBM
+ *   vv_crossfade_pcm / vv_batch_crossfade / vv_synthesize_joined
+ *       <- AudioProcessor.fix_clipped_audio + concatenate_with_crossfade_improved
+ *          (vietvoicetts/core/audio_processor.py:47-58,123-193; called at core/tts_engine.py:244-246)
  *   vv_get_tensor / vv_set_noise  <- numpy arrays handed between session.run calls (tts_engine.py:229-235)
  *   vv_last_error        <- the exception text wrapped at tts_engine.py:256-257 / model.py:125-129
  *
@@ -145,6 +148,25 @@ typedef struct vv_request {
  * in an LRU of VVB200_BATCH_CACHE entries (default 6); their buffers come from the device's stream-ordered memory
  * pool and all batches share one instantiated CUDA graph of the sampling loop per nfe, updated in place. */
 int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed);
+
+/* ---- cross-fade on the device --------------------------------------------------------------------------- */
+/* AudioProcessor.concatenate_with_crossfade_improved (vietvoicetts/core/audio_processor.py:123-193) with its per-chunk
+ * fix_clipped_audio (:47-58), bit-exact with the reference's numpy arithmetic: float64 clip fix, float32 level ratio
+ * from numpy's pairwise mean of squares (clipped to [0.7, 1.5], only when both RMS values exceed 100), float64
+ * cos^2 / sin^2 seam, every cast truncating toward zero.  fade_out / fade_in: the n_fade-point float64 tables exactly as
+ * the reference computes them — np.cos(np.linspace(0, pi/2, n_fade)) ** 2 and np.sin(...) ** 2 — passed in because
+ * libm and numpy differ in the last bit of cos / sin.  Every chunk must hold at least 2 * n_fade samples and n >= 2
+ * (otherwise VV_ERR_ARG: use the host path); the joined wave has sum(len) - n_fade * (n - 1) samples.
+ *   vv_crossfade_pcm     host chunks in, host wave out (e.g. waves gathered from several ranks)
+ *   vv_batch_crossfade   decoded chunks order[0..n) of a batch (order == NULL: 0..n-1), straight from device PCM
+ *   vv_synthesize_joined vv_synthesize_batch for the chunks of ONE text + the cross-fade in request order: only the
+ *                        joined wave is copied to the host (a single chunk is returned untouched, as upstream) */
+int vv_crossfade_pcm(vv_engine* e, const int16_t* const* waves, const int64_t* lens, int n, const double* fade_out,
+                     const double* fade_in, int n_fade, int16_t* pcm_out, int64_t capacity, int64_t* n_out);
+int vv_batch_crossfade(vv_batch* b, const int32_t* order, int n, const double* fade_out, const double* fade_in,
+                       int n_fade, int16_t* pcm_out, int64_t capacity, int64_t* n_out);
+int vv_synthesize_joined(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed, const double* fade_out,
+                         const double* fade_in, int n_fade, int16_t* pcm_out, int64_t capacity, int64_t* n_out);
 
 /* Same path with every input already resident in HBM (uploaded by a previous vv_preprocess of each chunk): recomputes
  * mel + text conditioning, restores y0, runs the (nfe-1)-step loop and the decode; PCM stays on the device

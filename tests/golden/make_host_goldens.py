@@ -108,6 +108,20 @@ def main():
     out["xf_improved_single"] = AP.concatenate_with_crossfade_improved(waves[:1], 0.1, 24000)
     out["xf_plain"] = AP.concatenate_with_crossfade(waves, 0.1, 24000)
     out["xf_plain_short"] = AP.concatenate_with_crossfade([waves[4], waves[2]], 0.1, 24000)
+    # regular regime of the fold (every chunk at least two fades long: what the device cross-fade covers): a loud, a
+    # clipped (+32767 and -32768 present), a quiet (RMS < 100: no level matching), a much louder (ratio clipped to 0.7)
+    # and a much softer chunk (ratio clipped to 1.5, wraps int16 where 1.5 x overflows), seven chunks in all
+    rr = np.random.default_rng(424242)
+    reg = []
+    for n, a in ((9000, 4000), (12000, 9000), (7000, 30), (10000, 15000), (6000, 700), (8000, 21000), (5000, 2500)):
+        reg.append(np.clip(rr.standard_normal(n) * a, -32768, 32767).astype(np.int16).reshape(1, 1, -1))
+    reg[1][0, 0, 77] = 32767
+    reg[1][0, 0, 78] = -32768
+    reg[5][0, 0, :2400] = np.clip(reg[5][0, 0, :2400].astype(np.int32) * 3 // 2, -32768, 32767).astype(np.int16)
+    for i, w in enumerate(reg):
+        out[f"xfr_wave{i}"] = w
+    out["xfr_out"] = AP.concatenate_with_crossfade_improved(reg, 0.1, 24000)
+    out["xfr_out_two"] = AP.concatenate_with_crossfade_improved(reg[3:5], 0.05, 24000)
     np.savez_compressed(os.path.join(HERE, "host_audio.npz"), **out)
 
     # ------------------------------------------------------------------ TTSEngine._prepare_inputs (core/tts_engine.py:43-131)

@@ -20,6 +20,6 @@ run conv 180 tests/test_kernels_gpu.py -m gpu -k "conv_rows"
 run ln 120 tests/test_kernels_gpu.py -m gpu -k "ln_modulate"
 run attn 240 tests/test_kernels_gpu.py -m gpu -k "attention"
 run engine 400 tests/test_engine_gpu.py -m gpu
-run prompt 300 tests/test_prompt_cache_gpu.py -m gpu
+run prompt 300 tests/test_prompt_cache_gpu.py tests/test_crossfade_gpu.py -m gpu
 run path 600 tests/test_path_gpu.py tests/test_configs_gpu.py tests/test_scheduler_gpu.py tests/test_edge_gpu.py -m gpu
 run parity_full 600 tests/test_parity_full_gpu.py -m gpu -s

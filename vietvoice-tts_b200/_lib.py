@@ -94,6 +94,9 @@ def load() -> C.CDLL:
             "vv_sync": (I, [P]),
             "vv_debug_partial_step": (I, [P, I, I, I]),
             "vv_synthesize_batch": (I, [P, C.POINTER(VVRequest), I, I, U64]),
+            "vv_crossfade_pcm": (I, [P, C.POINTER(P), C.POINTER(I64), I, P, P, I, P, I64, C.POINTER(I64)]),
+            "vv_batch_crossfade": (I, [P, C.POINTER(C.c_int32), I, P, P, I, P, I64, C.POINTER(I64)]),
+            "vv_synthesize_joined": (I, [P, C.POINTER(VVRequest), I, I, U64, P, P, I, P, I64, C.POINTER(I64)]),
             "vv_run_resident": (I, [P, I]),
             "vv_profile_step": (I, [P, I, I, C.POINTER(C.c_float)]),
             "vv_profile_stages": (I, [P, I, C.POINTER(C.c_float)]),

@@ -1756,9 +1756,11 @@ extern "C" int vv_set_cond(vv_batch* b, int idx, const float* cat_mel_text, cons
 }
 
 // ------------------------------------------------------------------------------------------------ whole path
-extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed) {
-  if (!e || !reqs || B <= 0) return fail(VV_ERR_ARG, "vv_synthesize_batch: bad argument");
-  ENG_LOCK(e);
+static int batch_crossfade(vv_batch* b, const int32_t* order, int n, const double* fo, const double* fi, int nf,
+                           int16_t* pcm_out, int64_t capacity, int64_t* n_out);
+
+// preprocess -> sampling loop -> decode for B requests on a cached batch; the PCM stays on the device
+static int synthesize_on_device(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed, vv_batch** out_b) {
   if (!e->finalized) return fail(VV_ERR_STATE, "engine not finalized");
   CK(cudaSetDevice(e->device));
   std::vector<int64_t> key(B);
@@ -1810,6 +1812,15 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
   if (nfe <= 0) nfe = e->a.nfe;
   TRY(vv_sample(b, nfe, 0, nfe - 1));
   TRY(decode_all(b));
+  *out_b = b;
+  return 0;
+}
+
+extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed) {
+  if (!e || !reqs || B <= 0) return fail(VV_ERR_ARG, "vv_synthesize_batch: bad argument");
+  ENG_LOCK(e);
+  vv_batch* b = nullptr;
+  TRY(synthesize_on_device(e, reqs, B, nfe, seed, &b));
   for (int i = 0; i < B; ++i) {
     if (reqs[i].pcm_capacity < b->pcm_len[i] || (!reqs[i].pcm_out && b->pcm_len[i] > 0))
       return fail(VV_ERR_ARG, "request %d: pcm_capacity %lld < %lld", i, (long long)reqs[i].pcm_capacity, (long long)b->pcm_len[i]);
@@ -1819,6 +1830,156 @@ extern "C" int vv_synthesize_batch(vv_engine* e, vv_request* reqs, int B, int nf
   }
   CK(cudaStreamSynchronize(e->st));
   return 0;
+}
+
+// vv_synthesize_batch for the chunks of ONE text, joined on the device: the requests are synthesized as a batch, then
+// clip-fixed and cross-faded in request order (vv_batch_crossfade); only the joined wave crosses PCIe.  The per-request
+// pcm_out / pcm_capacity fields are ignored.
+extern "C" int vv_synthesize_joined(vv_engine* e, vv_request* reqs, int B, int nfe, uint64_t seed, const double* fade_out,
+                                    const double* fade_in, int n_fade, int16_t* pcm_out, int64_t capacity,
+                                    int64_t* n_out) {
+  if (!e || !reqs || B <= 0 || !pcm_out) return fail(VV_ERR_ARG, "vv_synthesize_joined: bad argument");
+  ENG_LOCK(e);
+  vv_batch* b = nullptr;
+  TRY(synthesize_on_device(e, reqs, B, nfe, seed, &b));
+  for (int i = 0; i < B; ++i) reqs[i].n_out = b->pcm_len[i];
+  if (B == 1) {       // a single chunk is returned untouched (audio_processor.py:130-131)
+    if (capacity < b->pcm_len[0]) return fail(VV_ERR_ARG, "vv_synthesize_joined: capacity too small");
+    if (b->pcm_len[0] > 0)
+      CK(cudaMemcpyAsync(pcm_out, b->pcm_d + b->pcm_off[0], (size_t)b->pcm_len[0] * 2, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    if (n_out) *n_out = b->pcm_len[0];
+    return 0;
+  }
+  return batch_crossfade(b, nullptr, B, fade_out, fade_in, n_fade, pcm_out, capacity, n_out);
+}
+
+// ------------------------------------------------------------------------------------------------ cross-fade
+struct XfChunkH {          // = frontend.cu XfChunk
+  const int16_t* src;
+  int64_t len;
+  int64_t out_off;
+};
+static_assert(sizeof(XfChunkH) == 24, "XfChunk layout");
+
+// joins device-resident int16 chunks (src[i], lens[i]) into out_d; *total receives the joined length.
+// Preconditions checked by the callers: n >= 2, nf >= 1, every chunk holds at least 2 * nf samples.
+static int crossfade_device(vv_engine* e, const std::vector<const int16_t*>& src, const std::vector<int64_t>& lens, int nf,
+                            const double* fade_out_h, const double* fade_in_h, int16_t* out_d, int64_t* total) {
+  const int n = (int)src.size();
+  std::vector<XfChunkH> ch(n);
+  int64_t off = 0, max_len = 0;
+  for (int i = 0; i < n; ++i) {
+    ch[i].src = src[i];
+    ch[i].len = lens[i];
+    ch[i].out_off = off;
+    off += lens[i] - (i + 1 < n ? nf : 0);
+    max_len = std::max(max_len, lens[i]);
+  }
+  *total = off;
+  void* scratch = nullptr;
+  const size_t b_ch = (size_t)n * sizeof(XfChunkH), b_i = (size_t)n * 4, b_f = (size_t)nf * 8;
+  const size_t o_clip = (b_ch + 255) / 256 * 256, o_has = o_clip + (b_i + 255) / 256 * 256,
+               o_ratio = o_has + (b_i + 255) / 256 * 256, o_fo = o_ratio + (b_i + 255) / 256 * 256,
+               o_fi = o_fo + (b_f + 255) / 256 * 256, bytes = o_fi + b_f;
+  CK(cudaMallocAsync(&scratch, bytes, e->st));
+  uint8_t* s8 = static_cast<uint8_t*>(scratch);
+  CK(cudaMemcpyAsync(s8, ch.data(), b_ch, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(s8 + o_fo, fade_out_h, b_f, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(s8 + o_fi, fade_in_h, b_f, cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));      // `ch` is a pageable host vector that dies with this frame
+  launch_crossfade(s8, n, max_len, nf, reinterpret_cast<const double*>(s8 + o_fo),
+                   reinterpret_cast<const double*>(s8 + o_fi), reinterpret_cast<int*>(s8 + o_clip),
+                   reinterpret_cast<int*>(s8 + o_has), reinterpret_cast<float*>(s8 + o_ratio), out_d, e->st);
+  e->launches += 3;
+  CK(cudaFreeAsync(scratch, e->st));
+  CKL();
+  return 0;
+}
+
+static int crossfade_args_ok(int n, int nf, const double* fo, const double* fi) {
+  if (n < 2 || nf < 1 || nf > 6144 || !fo || !fi)
+    return fail(VV_ERR_ARG, "cross-fade needs >= 2 chunks, 1..6144 fade samples and both fade tables");
+  return 0;
+}
+
+extern "C" int vv_crossfade_pcm(vv_engine* e, const int16_t* const* waves, const int64_t* lens, int n,
+                                const double* fade_out, const double* fade_in, int n_fade, int16_t* pcm_out,
+                                int64_t capacity, int64_t* n_out) {
+  if (!e || !waves || !lens || !pcm_out) return fail(VV_ERR_ARG, "vv_crossfade_pcm: null argument");
+  TRY(crossfade_args_ok(n, n_fade, fade_out, fade_in));
+  ENG_LOCK(e);
+  CK(cudaSetDevice(e->device));
+  int64_t sum = 0;
+  for (int i = 0; i < n; ++i) {
+    if (lens[i] < 2 * (int64_t)n_fade) return fail(VV_ERR_ARG, "chunk %d holds %lld samples, fewer than two cross-fades", i, (long long)lens[i]);
+    sum += lens[i];
+  }
+  const int64_t total = sum - (int64_t)n_fade * (n - 1);
+  if (capacity < total) return fail(VV_ERR_ARG, "vv_crossfade_pcm: capacity %lld < %lld", (long long)capacity, (long long)total);
+  int16_t *in_d = nullptr, *out_d = nullptr;
+  CK(cudaMallocAsync(&in_d, (size_t)sum * 2, e->st));
+  CK(cudaMallocAsync(&out_d, (size_t)total * 2, e->st));
+  std::vector<const int16_t*> src(n);
+  std::vector<int64_t> ln(lens, lens + n);
+  int64_t o = 0;
+  for (int i = 0; i < n; ++i) {
+    CK(cudaMemcpyAsync(in_d + o, waves[i], (size_t)lens[i] * 2, cudaMemcpyHostToDevice, e->st));
+    src[i] = in_d + o;
+    o += lens[i];
+  }
+  int64_t got = 0;
+  int rc = crossfade_device(e, src, ln, n_fade, fade_out, fade_in, out_d, &got);
+  if (rc == 0) {
+    cudaMemcpyAsync(pcm_out, out_d, (size_t)got * 2, cudaMemcpyDeviceToHost, e->st);
+    if (n_out) *n_out = got;
+  }
+  cudaFreeAsync(in_d, e->st);
+  cudaFreeAsync(out_d, e->st);
+  CK(cudaStreamSynchronize(e->st));
+  return rc;
+}
+
+// cross-fade of the decoded chunks order[0..n) of a batch, straight from its device PCM
+static int batch_crossfade(vv_batch* b, const int32_t* order, int n, const double* fo, const double* fi, int nf,
+                           int16_t* pcm_out, int64_t capacity, int64_t* n_out) {
+  vv_engine* e = b->e;
+  TRY(crossfade_args_ok(n, nf, fo, fi));
+  TRY(decode_all(b));
+  std::vector<const int16_t*> src(n);
+  std::vector<int64_t> ln(n);
+  int64_t sum = 0;
+  for (int i = 0; i < n; ++i) {
+    const int c = order ? order[i] : i;
+    if (c < 0 || c >= b->B) return fail(VV_ERR_ARG, "cross-fade: chunk index %d out of range", c);
+    if (b->pcm_len[c] < 2 * (int64_t)nf)
+      return fail(VV_ERR_ARG, "chunk %d holds %lld samples, fewer than two cross-fades", c, (long long)b->pcm_len[c]);
+    src[i] = b->pcm_d + b->pcm_off[c];
+    ln[i] = b->pcm_len[c];
+    sum += ln[i];
+  }
+  const int64_t total = sum - (int64_t)nf * (n - 1);
+  if (capacity < total) return fail(VV_ERR_ARG, "cross-fade: capacity %lld < %lld", (long long)capacity, (long long)total);
+  int16_t* out_d = nullptr;
+  CK(cudaMallocAsync(&out_d, (size_t)total * 2, e->st));
+  int64_t got = 0;
+  int rc = crossfade_device(e, src, ln, nf, fo, fi, out_d, &got);
+  if (rc == 0) {
+    cudaMemcpyAsync(pcm_out, out_d, (size_t)got * 2, cudaMemcpyDeviceToHost, e->st);
+    if (n_out) *n_out = got;
+  }
+  cudaFreeAsync(out_d, e->st);
+  CK(cudaStreamSynchronize(e->st));
+  return rc;
+}
+
+extern "C" int vv_batch_crossfade(vv_batch* b, const int32_t* order, int n, const double* fade_out,
+                                  const double* fade_in, int n_fade, int16_t* pcm_out, int64_t capacity,
+                                  int64_t* n_out) {
+  if (!b || !b->e || !pcm_out) return fail(VV_ERR_ARG, "vv_batch_crossfade: null argument");
+  ENG_LOCK(b->e);
+  CK(cudaSetDevice(b->e->device));
+  return batch_crossfade(b, order, n, fade_out, fade_in, n_fade, pcm_out, capacity, n_out);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel-level ABI

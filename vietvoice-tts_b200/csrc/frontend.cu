@@ -385,6 +385,148 @@ void launch_istft_ola(const float* head, int ld_head, const float* hann, const f
   istft_ola_kernel<<<grid, 256, 0, st>>>(head, ld_head, hann, tw, mag_clip, dec_off, dec_len, pcm_off, pcm_scale, pcm);
 }
 
+// ------------------------------------------------------------------------------------------------ cross-fade
+// Clip-fix + RMS-matched cos^2 / sin^2 cross-fade of a list of int16 chunks, bit-exact with the reference's numpy code
+// (/root/reference/vietvoicetts/core/audio_processor.py: fix_clipped_audio :47-58,
+// concatenate_with_crossfade_improved :123-193).  What "bit-exact" needs:
+//   * np.abs on int16 leaves -32768 negative, so only +-32767 trips the clip fix; the fix multiplies in float64;
+//   * the level ratio is float32 arithmetic on np.mean(x.astype(float32) ** 2), and numpy sums float32 arrays
+//     PAIRWISE (blocks of <= 128 elements with 8 interleaved accumulators, halves split at multiples of 8): the same
+//     tree is walked here;
+//   * every float -> int16 cast truncates toward zero and wraps modulo 2^16 (a ratio of 1.5 can overflow int16: the
+//     reference wraps, so do we);
+//   * the fade tables are float64 and are computed by numpy on the host (cos / sin differ in the last bit between
+//     libraries), multiplied and added without FMA contraction.
+// The fold is sequential only through the level ratio: ratio[i] depends on the tail of chunk i-1 AFTER its own
+// adjustment.  One block walks the junctions (xf_ratio_kernel); the samples are then written fully in parallel.
+struct XfChunk {
+  const int16_t* src;
+  int64_t len;
+  int64_t out_off;     // where sample 0 of this chunk lands in the joined wave
+};
+
+__device__ __forceinline__ int16_t xf_fixed(int16_t v, int clipped) {
+  if (!clipped) return v;
+  const double s = __dmul_rn((double)v, 26214.0 / 32767.0);
+  return (int16_t)(int32_t)s;                       // trunc toward zero
+}
+__device__ __forceinline__ int16_t xf_adjusted(int16_t fixed, int has_ratio, float ratio) {
+  if (!has_ratio) return fixed;
+  return (int16_t)__float2int_rz(__fmul_rn((float)fixed, ratio));     // wraps like the numpy cast
+}
+
+__global__ void __launch_bounds__(1024) xf_clip_kernel(const XfChunk* __restrict__ ch, int* __restrict__ clipped) {
+  __shared__ int red[32];
+  const XfChunk c = ch[blockIdx.x];
+  int mx = -32768;
+  for (int64_t i = threadIdx.x; i < c.len; i += blockDim.x) {
+    const int v = c.src[i];
+    const int a = v == -32768 ? -32768 : (v < 0 ? -v : v);           // np.abs(int16)
+    mx = max(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) clipped[blockIdx.x] = mx >= 32767 ? 1 : 0;
+  }
+}
+
+// numpy's pairwise float32 sum (numpy/_core/src/umath/loops_utils.h.src), same association order
+__device__ float xf_pairwise_sum(const float* a, int n) {
+  if (n < 8) {
+    float r = 0.f;
+    for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(xf_pairwise_sum(a, n2), xf_pairwise_sum(a + n2, n - n2));
+}
+
+// one block: for every junction i = 1 .. n-1 the level ratio of chunk i (has[i] = 0: levels too low, no adjustment)
+__global__ void __launch_bounds__(256) xf_ratio_kernel(const XfChunk* __restrict__ ch, const int* __restrict__ clipped,
+                                                       int n, int nf, int* __restrict__ has, float* __restrict__ ratio) {
+  extern __shared__ float sq[];                     // [2][nf]: squares of the previous tail, of the next head
+  __shared__ int s_has;
+  __shared__ float s_ratio;
+  if (threadIdx.x == 0) { s_has = 0; s_ratio = 1.f; has[0] = 0; ratio[0] = 1.f; }
+  __syncthreads();
+  for (int i = 1; i < n; ++i) {
+    const XfChunk p = ch[i - 1], c = ch[i];
+    const int ph = s_has;
+    const float pr = s_ratio;
+    const int pc = clipped[i - 1], cc = clipped[i];
+    for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+      const float a = (float)xf_adjusted(xf_fixed(p.src[p.len - nf + k], pc), ph, pr);
+      const float b = (float)xf_fixed(c.src[k], cc);
+      sq[k] = __fmul_rn(a, a);
+      sq[nf + k] = __fmul_rn(b, b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float rp = __fsqrt_rn(__fdiv_rn(xf_pairwise_sum(sq, nf), (float)nf));
+      const float rn = __fsqrt_rn(__fdiv_rn(xf_pairwise_sum(sq + nf, nf), (float)nf));
+      int h = 0;
+      float r = 1.f;
+      if (rp > 100.f && rn > 100.f) {
+        h = 1;
+        r = fminf(fmaxf(__fdiv_rn(rp, rn), 0.7f), 1.5f);
+      }
+      s_has = h; s_ratio = r;
+      has[i] = h; ratio[i] = r;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) xf_apply_kernel(const XfChunk* __restrict__ ch, const int* __restrict__ clipped,
+                                                       const int* __restrict__ has, const float* __restrict__ ratio,
+                                                       int n, int nf, const double* __restrict__ fade_out,
+                                                       const double* __restrict__ fade_in, int16_t* __restrict__ out) {
+  const int i = blockIdx.y;
+  const XfChunk c = ch[i];
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= c.len) return;
+  if (i + 1 < n && k >= c.len - nf) return;                 // the tail is written as the next chunk's seam
+  const int16_t a = xf_adjusted(xf_fixed(c.src[k], clipped[i]), has[i], ratio[i]);
+  if (i > 0 && k < nf) {
+    const XfChunk p = ch[i - 1];
+    const int16_t t = xf_adjusted(xf_fixed(p.src[p.len - nf + k], clipped[i - 1]), has[i - 1], ratio[i - 1]);
+    const double v = __dadd_rn(__dmul_rn((double)(float)t, fade_out[k]), __dmul_rn((double)(float)a, fade_in[k]));
+    out[c.out_off + k] = (int16_t)(int32_t)v;
+  } else {
+    out[c.out_off + k] = a;
+  }
+}
+
+void launch_crossfade(const void* chunks, int n, int64_t max_len, int nf, const double* fade_out, const double* fade_in,
+                      int* clipped, int* has, float* ratio, int16_t* out, cudaStream_t st) {
+  const XfChunk* ch = static_cast<const XfChunk*>(chunks);
+  xf_clip_kernel<<<n, 1024, 0, st>>>(ch, clipped);
+  xf_ratio_kernel<<<1, 256, (size_t)2 * nf * sizeof(float), st>>>(ch, clipped, n, nf, has, ratio);
+  dim3 grid((unsigned)((max_len + 255) / 256), n);
+  xf_apply_kernel<<<grid, 256, 0, st>>>(ch, clipped, has, ratio, n, nf, fade_out, fade_in, out);
+}
+
 // ------------------------------------------------------------------------------------------------ weight layout
 // conv_pos weight [dim, cg, taps] fp32 -> bf16 [groups][taps][co(cg)][ci(cg)]
 __global__ void permute_conv_w_kernel(const float* __restrict__ w, int dim, int cg, int taps, bf16* __restrict__ out) {

@@ -25,6 +25,10 @@ void launch_voc_im2col(const float* mel, const int32_t* src_row, const int32_t* 
 void launch_istft_ola(const float* head, int ld_head, const float* hann, const float2* tw, float mag_clip,
                       const int32_t* dec_off, const int32_t* dec_len, const int64_t* pcm_off, int n_chunks,
                       int max_frames, float pcm_scale, int16_t* pcm, cudaStream_t st);
+// chunks: device array of n {const int16_t* src; int64_t len; int64_t out_off} records (frontend.cu XfChunk);
+// clipped / has / ratio: n-element scratch; nf: cross-fade samples (every chunk must hold >= 2 * nf samples)
+void launch_crossfade(const void* chunks, int n, int64_t max_len, int nf, const double* fade_out, const double* fade_in,
+                      int* clipped, int* has, float* ratio, int16_t* out, cudaStream_t st);
 void launch_permute_conv_w(const float* w, int dim, int cg, int taps, bf16* out, cudaStream_t st);
 void launch_permute_embed_w(const float* w, int vd, int n_mel, int K, int ld, bf16* out, cudaStream_t st);
 

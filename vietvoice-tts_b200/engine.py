@@ -20,6 +20,14 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def fade_tables(n_fade: int):
+    """The float64 cos^2 / sin^2 fade tables exactly as the reference computes them
+    (/root/reference/vietvoicetts/core/audio_processor.py:175-176); numpy evaluates them on the host because cos / sin
+    differ in the last bit between math libraries and the device cross-fade must reproduce the host's bits."""
+    theta = np.linspace(0, np.pi / 2, n_fade)
+    return np.ascontiguousarray(np.cos(theta) ** 2), np.ascontiguousarray(np.sin(theta) ** 2)
+
+
 class Engine:
     def __init__(self, arch: ArchConfig, device: int = 0, stream: Optional[int] = None):
         arch.validate()
@@ -115,15 +123,35 @@ class Engine:
         _lib.check(self.lib.vv_prompt_cache_stats(self._h, w))
         return {"resident": int(w[0]), "uploads": int(w[1]), "hits": int(w[2])}
 
+    # -- cross-fade on the device ------------------------------------------------
+    def crossfade_ok(self, lengths: Sequence[int], n_fade: int) -> bool:
+        """the device cross-fade covers the regular case: >= 2 chunks, each at least two fades long"""
+        return len(lengths) >= 2 and 1 <= n_fade <= 6144 and all(int(n) >= 2 * n_fade for n in lengths)
+
+    def crossfade_pcm(self, waves: Sequence[np.ndarray], n_fade: int) -> np.ndarray:
+        """`concatenate_with_crossfade_improved` of host int16 chunks, computed on the GPU, bit-exact with numpy."""
+        ws = [np.ascontiguousarray(np.asarray(w).reshape(-1), dtype=np.int16) for w in waves]
+        n = len(ws)
+        fo, fi = fade_tables(n_fade)
+        ptrs = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+        lens = (C.c_int64 * n)(*[w.size for w in ws])
+        out = np.empty(sum(w.size for w in ws), dtype=np.int16)
+        got = C.c_int64(0)
+        _lib.check(self.lib.vv_crossfade_pcm(self._h, ptrs, lens, n, _ptr(fo), _ptr(fi), n_fade, _ptr(out), out.size,
+                                             C.byref(got)))
+        return out[: int(got.value)]
+
     # -- whole path, host buffers ------------------------------------------------------------------
     def synthesize_batch(self, audios: Sequence[np.ndarray], text_ids: Sequence[np.ndarray],
                          total_frames: Sequence[int], noises: Optional[Sequence[Optional[np.ndarray]]] = None,
                          nfe: int = 0, seed: int = 9527, chunk_keys: Optional[Sequence[int]] = None,
                          pcm_out: Optional[Sequence[np.ndarray]] = None,
-                         prompt_ids: Optional[Sequence[int]] = None) -> List[np.ndarray]:
+                         prompt_ids: Optional[Sequence[int]] = None, join_fade: int = 0):
         """One call = preprocess -> (nfe-1) steps -> decode for B chunks; host arrays in, int16 PCM out.
         `prompt_ids[i]` (from `prompt_put`) names a resident prompt; without it the engine finds the prompt by hashing
-        audios[i] — chunks that pass the SAME array object are hashed once."""
+        audios[i] — chunks that pass the SAME array object are hashed once.
+        `join_fade` > 0: the chunks are those of ONE text, in order — they are clip-fixed and cross-faded over
+        `join_fade` samples on the device and ONE joined int16 wave is returned (a single chunk comes back untouched)."""
         B = len(audios)
         reqs = (_lib.VVRequest * B)()
         keep = []
@@ -165,6 +193,13 @@ class Engine:
             else:
                 reqs[i].prompt_id = shared.get(id(audios[i]), 0)
             outs.append(o)
+        if join_fade > 0:
+            fo, fi = fade_tables(join_fade)
+            joined = np.empty(sum(o.size for o in outs), dtype=np.int16)
+            got = C.c_int64(0)
+            _lib.check(self.lib.vv_synthesize_joined(self._h, reqs, B, nfe, seed, _ptr(fo), _ptr(fi), join_fade,
+                                                     _ptr(joined), joined.size, C.byref(got)))
+            return joined[: int(got.value)]
         _lib.check(self.lib.vv_synthesize_batch(self._h, reqs, B, nfe, seed))
         return [outs[i][: int(reqs[i].n_out)] for i in range(B)]
 
@@ -238,6 +273,18 @@ class Batch:
 
     def debug_partial_step(self, step: int, n_layers: int, nfe: int = 0) -> None:
         _lib.check(self.lib.vv_debug_partial_step(self._h, nfe, step, n_layers))
+
+    def crossfade(self, n_fade: int, order: Optional[Sequence[int]] = None) -> np.ndarray:
+        """clip-fix + cross-fade of the decoded chunks (all, or `order`) straight from device PCM -> joined int16 wave"""
+        idx = list(range(self.B)) if order is None else [int(i) for i in order]
+        fo, fi = fade_tables(n_fade)
+        cap = sum(int(self.lib.vv_batch_pcm_len(self._h, i)) for i in idx)
+        out = np.empty(max(cap, 1), dtype=np.int16)
+        arr = (C.c_int32 * len(idx))(*idx)
+        got = C.c_int64(0)
+        _lib.check(self.lib.vv_batch_crossfade(self._h, arr, len(idx), _ptr(fo), _ptr(fi), n_fade, _ptr(out), out.size,
+                                               C.byref(got)))
+        return out[: int(got.value)]
 
     def decode(self, idx: int) -> np.ndarray:
         n = int(self.lib.vv_batch_pcm_len(self._h, idx))

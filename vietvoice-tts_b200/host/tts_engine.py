@@ -39,6 +39,7 @@ class TTSEngine:
         self.use_sessions = use_sessions
         self.shard = shard               # optional vietvoice_tts_b200.shard.Sharder
         self.last_timing: dict = {}      # seconds per stage of the last synthesize() call (bench / logging only)
+        self.gpu_crossfade = True        # unsharded multi-chunk texts: clip-fix + cross-fade on the device
 
     def cleanup(self) -> None:
         if self.model_session_manager:
@@ -159,6 +160,29 @@ class TTSEngine:
         self.last_timing.update(synth_s=t1 - t0, gather_s=time.time() - t1, n_chunks=n, local_chunks=len(mine))
         return [local[i] for i in range(n)]
 
+    def _synthesize_joined(self, inputs_list) -> Optional[np.ndarray]:
+        """All chunks of the text as one batch AND the reference's clip-fix / cross-fade fold
+        (/root/reference/vietvoicetts/core/audio_processor.py:123-193) on the GPU, bit-exact with the host code: only
+        the joined wave is copied back.  Returns None when the case is not the regular one (sharded over ranks, fewer
+        than two chunks worth fading, a chunk shorter than two fades) — the caller then takes the host fold."""
+        if self.shard is not None or not self.gpu_crossfade or len(inputs_list) < 2:
+            return None
+        cfg = self.config
+        eng = self.model_session_manager.engine
+        n_fade = int(cfg.cross_fade_duration * cfg.sample_rate)
+        ref_frames = inputs_list[0][0].shape[-1] // cfg.hop_length + 1
+        lengths = [max(0, int(i[2][0]) - ref_frames - 1) * cfg.hop_length for i in inputs_list]
+        if not eng.crossfade_ok(lengths, n_fade):
+            return None
+        t0 = time.time()
+        keys = list(range(len(inputs_list)))
+        wave = eng.synthesize_batch([i[0] for i in inputs_list], [i[1] for i in inputs_list],
+                                    [int(i[2][0]) for i in inputs_list], nfe=cfg.nfe_step, seed=cfg.random_seed,
+                                    chunk_keys=keys, join_fade=n_fade)
+        self.last_timing.update(synth_s=time.time() - t0, gather_s=0.0, n_chunks=len(keys), local_chunks=len(keys),
+                                crossfade="device")
+        return wave
+
     def synthesize(self, text: str, gender: Optional[str] = None, group: Optional[str] = None,
                    area: Optional[str] = None, emotion: Optional[str] = None, sample_iteration: Optional[int] = None,
                    output_path: Optional[str] = None, reference_audio: Optional[str] = None,
@@ -171,13 +195,16 @@ class TTSEngine:
             self.last_timing = {}
             inputs_list = self._prepare_inputs(ref_audio, ref_text, text)
             t1 = time.time()
+            final = None
             if self.use_sessions or self.config.fuse_nfe != 1:
                 waves = self._synthesize_chunks_sessions(inputs_list)
             else:
-                waves = self._synthesize_chunks_batched(inputs_list)
+                final = self._synthesize_joined(inputs_list)          # batch + clip-fix + cross-fade on the device
+                waves = None if final is not None else self._synthesize_chunks_batched(inputs_list)
             t2 = time.time()
-            final = self.audio_processor.concatenate_with_crossfade_improved(
-                waves, self.config.cross_fade_duration, self.config.sample_rate)
+            if final is None:
+                final = self.audio_processor.concatenate_with_crossfade_improved(
+                    waves, self.config.cross_fade_duration, self.config.sample_rate)
             elapsed = time.time() - t0
             self.last_timing.update(prepare_s=t1 - t0, crossfade_s=time.time() - t2, total_s=elapsed)
             if output_path:
