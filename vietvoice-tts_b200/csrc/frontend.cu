@@ -35,7 +35,21 @@ __global__ void __launch_bounds__(1024) rms_scale_kernel(const int16_t* __restri
                                                          float target_rms, float* __restrict__ scale_out) {
   __shared__ float red[32];
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  // eight samples per 16-byte load (the PCM buffer comes from the allocator: 256-byte aligned), scalar tail
+  const int64_t n8 = ((reinterpret_cast<uintptr_t>(audio) & 15) == 0) ? n / 8 : 0;
+  const uint4* a8 = reinterpret_cast<const uint4*>(audio);
+  for (int64_t i = threadIdx.x; i < n8; i += blockDim.x) {
+    const uint4 u = __ldg(a8 + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = (float)(int16_t)(w[k] & 0xffffu) * (1.0f / 32768.0f);
+      const float hi = (float)(int16_t)(w[k] >> 16) * (1.0f / 32768.0f);
+      s += lo * lo;
+      s += hi * hi;
+    }
+  }
+  for (int64_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
     const float v = (float)audio[i] * (1.0f / 32768.0f);
     s += v * v;
   }
@@ -131,10 +145,45 @@ __global__ void dwconv_rows_kernel(const float* __restrict__ x, const int32_t* _
   }
   out[i] = acc;
 }
+// the same, four channels per thread (C % 4 == 0, K <= 8): 16-byte loads / stores, the taps of the four channels in
+// registers.  Bandwidth-bound: a row is read once from HBM and 7x from L1/L2 by its neighbours.
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_rows4_kernel(const float4* __restrict__ x, const int32_t* __restrict__ row_pos,
+                    const int32_t* __restrict__ row_len, const float* __restrict__ w, const float* __restrict__ b,
+                    int rows, int C4, float4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * C4) return;
+  const int r = i / C4, c4 = i - (size_t)r * C4;
+  const int pos = row_pos[r], len = row_len[r];
+  float wk[4][K];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[j][k] = __ldg(w + (size_t)(c4 * 4 + j) * K + k);
+  float4 acc = __ldg(reinterpret_cast<const float4*>(b) + c4);
+  constexpr int h = K / 2;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int p = pos + k - h;
+    if (p >= 0 && p < len) {
+      const float4 v = x[(size_t)(r + k - h) * C4 + c4];
+      acc.x += wk[0][k] * v.x; acc.y += wk[1][k] * v.y; acc.z += wk[2][k] * v.z; acc.w += wk[3][k] * v.w;
+    }
+  }
+  out[i] = acc;
+}
 void launch_dwconv_rows(const float* x, const int32_t* row_pos, const int32_t* row_len, const float* w,
                         const float* b, int rows, int C, int K, float* out, cudaStream_t st) {
   const size_t n = (size_t)rows * C;
-  if (n) dwconv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, row_pos, row_len, w, b, rows, C, K, out);
+  if (!n) return;
+  if (K == 7 && C % 4 == 0) {
+    const size_t n4 = n / 4;
+    dwconv_rows4_kernel<7><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(x), row_pos, row_len, w, b, rows, C / 4, reinterpret_cast<float4*>(out));
+    return;
+  }
+  dwconv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, row_pos, row_len, w, b, rows, C, K, out);
 }
 
 // GRN (ConvNeXt-V2): per sequence, per channel L2 norm over TIME.  Two-stage reduction with a fixed summation
@@ -196,6 +245,30 @@ __global__ void grn_apply_kernel(const float* __restrict__ h, const int32_t* __r
   }
   out[i] = __float2bfloat16(v);
 }
+// four channels per thread: one 16-byte load of h, one 8-byte store of bf16
+__global__ void __launch_bounds__(256)
+grn_apply4_kernel(const float4* __restrict__ h, const int32_t* __restrict__ row_seq, const float* __restrict__ nx,
+                  const float* __restrict__ g, const float* __restrict__ b, int rows, int C4, uint2* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * C4) return;
+  const int r = i / C4, c4 = i - (size_t)r * C4;
+  const int seq = row_seq[r];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (seq >= 0) {
+    const float4 x = h[i];
+    const float4 n4 = __ldg(reinterpret_cast<const float4*>(nx + (size_t)seq * C4 * 4) + c4);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + c4);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + c4);
+    v.x = g4.x * (x.x * n4.x) + b4.x + x.x;
+    v.y = g4.y * (x.y * n4.y) + b4.y + x.y;
+    v.z = g4.z * (x.z * n4.z) + b4.z + x.z;
+    v.w = g4.w * (x.w * n4.w) + b4.w + x.w;
+  }
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y);
+  u.y = pack_bf16(v.z, v.w);
+  out[i] = u;
+}
 void launch_grn(const float* h, const int32_t* seq_off, const int32_t* seq_len, const int32_t* row_seq, int n_seq,
                 int max_len, int rows, int C, const float* g, const float* b, float* gx2, float* nx, bf16* out,
                 cudaStream_t st) {
@@ -205,7 +278,11 @@ void launch_grn(const float* h, const int32_t* seq_off, const int32_t* seq_len, 
   grn_sumsq_kernel<<<grid, 128, 0, st>>>(h, seq_off, seq_len, C, rpb, gx2);
   grn_norm_kernel<<<n_seq, 256, 0, st>>>(gx2, grid.y, C, nx);
   const size_t n = (size_t)rows * C;
-  grn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, row_seq, nx, g, b, rows, C, out);
+  if (C % 4 == 0)
+    grn_apply4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(h), row_seq, nx, g, b,
+                                                                      rows, C / 4, reinterpret_cast<uint2*>(out));
+  else
+    grn_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, row_seq, nx, g, b, rows, C, out);
 }
 
 // cat_b[row, :] = [ mel (cond rows) or 0 (uncond rows) | text | zero pad ]  -> bf16 [rows, ld]

@@ -160,12 +160,26 @@ class TTSEngine:
         self.last_timing.update(synth_s=t1 - t0, gather_s=time.time() - t1, n_chunks=n, local_chunks=len(mine))
         return [local[i] for i in range(n)]
 
+    def _fold(self, waves: List[np.ndarray]) -> np.ndarray:
+        """The reference's clip-fix / cross-fade fold over the ordered chunk list (core/tts_engine.py:244-246).  Waves
+        gathered from several ranks are folded on this rank's GPU when the case is the regular one (bit-exact with
+        the host code, ~10x faster than numpy for a 40-chunk text); otherwise on the host."""
+        cfg = self.config
+        n_fade = int(cfg.cross_fade_duration * cfg.sample_rate)
+        if self.gpu_crossfade and not self.use_sessions and len(waves) >= 2:
+            eng = self.model_session_manager.engine
+            if eng.crossfade_ok([w.size for w in waves], n_fade) and all(w.dtype == np.int16 for w in waves):
+                self.last_timing["crossfade"] = "device (gathered waves)"
+                return eng.crossfade_pcm(waves, n_fade)
+        self.last_timing["crossfade"] = "host"
+        return self.audio_processor.concatenate_with_crossfade_improved(waves, cfg.cross_fade_duration, cfg.sample_rate)
+
     def _synthesize_joined(self, inputs_list) -> Optional[np.ndarray]:
         """All chunks of the text as one batch AND the reference's clip-fix / cross-fade fold
         (/root/reference/vietvoicetts/core/audio_processor.py:123-193) on the GPU, bit-exact with the host code: only
         the joined wave is copied back.  Returns None when the case is not the regular one (sharded over ranks, fewer
         than two chunks worth fading, a chunk shorter than two fades) — the caller then takes the host fold."""
-        if self.shard is not None or not self.gpu_crossfade or len(inputs_list) < 2:
+        if (self.shard is not None and self.shard.world > 1) or not self.gpu_crossfade or len(inputs_list) < 2:
             return None
         cfg = self.config
         eng = self.model_session_manager.engine
@@ -203,8 +217,7 @@ class TTSEngine:
                 waves = None if final is not None else self._synthesize_chunks_batched(inputs_list)
             t2 = time.time()
             if final is None:
-                final = self.audio_processor.concatenate_with_crossfade_improved(
-                    waves, self.config.cross_fade_duration, self.config.sample_rate)
+                final = self._fold(waves)
             elapsed = time.time() - t0
             self.last_timing.update(prepare_s=t1 - t0, crossfade_s=time.time() - t2, total_s=elapsed)
             if output_path:
