@@ -540,6 +540,7 @@ bool launch_attention_split(const CUtensorMap& tmQKV, const AttnParams& p, cudaS
     const char* v = getenv("VVB200_ATTN");
     if (!v || !v[0]) return VV_ATTN_DEFAULT;
     if (!strcmp(v, "1")) return 0;
+    if (!strcmp(v, "3")) return 3;
     if (!strcmp(v, "96")) return 960;
     if (!strcmp(v, "96p")) return 961;
     if (!strcmp(v, "112")) return 1120;
@@ -553,6 +554,7 @@ bool launch_attention_split(const CUtensorMap& tmQKV, const AttnParams& p, cudaS
   }();
   if (mode == 0 || p.n_tiles <= 0) return mode != 0;
   switch (mode) {
+    case 3: launch_attention_gen3(tmQKV, p, st); break;
     case 960: launch_split<96, 0, false>(tmQKV, p, st); break;
     case 961: launch_split<96, 1, false>(tmQKV, p, st); break;
     case 1120: launch_split<112, 0, false>(tmQKV, p, st); break;

@@ -128,6 +128,8 @@ void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_
 #define VV_ATTN_DEFAULT 0
 #endif
 bool launch_attention_split(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
+// generation 3 (attn3.cu): generation 1 with the S readout of the next tile folded into the exp2 loop
+void launch_attention_gen3(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
 
 // LayerNorm (no affine) + AdaLN modulation: out = LN(x)*(1+scale)+shift -> bf16.  One warp per row.
 // If x2 != null computes the CFG-combined row:  (1+cfg)*h(x) - cfg*h(x2)   (used by nobody yet)
