@@ -74,7 +74,7 @@ lib.vv_engine_destroy(h)
 if what in ("attn", "all") and hasattr(lib, "vv_attn_trace_dump"):
     lib.vv_attn_trace_dump(b"gpurun_out/attn_trace.csv")
 if what in ("attn", "all"):
-    for name in ("vv_attn_timing_dump", "vv_attn2_timing_dump", "vv_attn3_timing_dump"):
+    for name in ("vv_attn_timing_dump",):
         if hasattr(lib, name):
             sys.stdout.flush()
             getattr(lib, name)()

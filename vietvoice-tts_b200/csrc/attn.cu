@@ -405,9 +405,6 @@ extern "C" void vv_attn_trace_dump(const char* path) {
 #endif
 
 int attn_q_tile() { return 128; }
-void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) {
-  if (launch_attention_split(tmQKV, p, st)) return;
-  launch_attention_impl(tmQKV, p, st);
-}
+void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st) { launch_attention_impl(tmQKV, p, st); }
 
 }  // namespace vv

@@ -122,14 +122,7 @@ struct AttnParams {
 };
 int attn_q_tile();    // query rows per tile_q0 entry expected by launch_attention (128)
 void launch_attention(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
-// generation 2 (attn2.cu): the exponentials of a row split between a MUFU thread and an FMA-pipe thread.  Returns
-// false when generation 1 (attn.cu) is selected (VVB200_ATTN=1, or VV_ATTN_DEFAULT == 0 and no override).
-#ifndef VV_ATTN_DEFAULT
-#define VV_ATTN_DEFAULT 0
-#endif
-bool launch_attention_split(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
-// generation 3 (attn3.cu): generation 1 with the S readout of the next tile folded into the exp2 loop
-void launch_attention_gen3(const CUtensorMap& tmQKV, const AttnParams& p, cudaStream_t st);
+
 
 // LayerNorm (no affine) + AdaLN modulation: out = LN(x)*(1+scale)+shift -> bf16.  One warp per row.
 // If x2 != null computes the CFG-combined row:  (1+cfg)*h(x) - cfg*h(x2)   (used by nobody yet)
