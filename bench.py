@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-WORK = dict(B=8, prompt_samples=144000, target_seconds=10.0, n_ids=270, nfe=32)
+WORK = dict(B=int(os.environ.get("VVB200_BENCH_B", "8")), prompt_samples=144000, target_seconds=10.0, n_ids=270, nfe=32)   # B != 8: experiments only
 
 
 def workload_dims(arch):
