@@ -44,8 +44,12 @@ def _worker(rank, world, port, q):
         ok = sorted(allw) == list(range(len(frames))) and all(
             allw[i].dtype == np.int16 and allw[i].shape[-1] == (frames[i] - 564) * 256 and int(allw[i][0, 0, 0]) == i
             for i in range(len(frames)))
+        # anything that is not a flat int16 wave (the engine never produces such, a caller might) takes the pickled path
+        allf = sh.gather({i: np.full((2, 3), i, dtype=np.float32) for i in mine}, len(frames))
+        ok = ok and sorted(allf) == list(range(len(frames))) and all(
+            allf[i].dtype == np.float32 and allf[i].shape == (2, 3) and float(allf[i][1, 2]) == i for i in allf)
         # a rank whose synthesis failed still joins the collective: the error surfaces on EVERY rank at once
-        # instead of leaving the healthy ranks blocked in all_gather_object until the gloo timeout
+        # instead of leaving the healthy ranks blocked in the collective until the gloo timeout
         try:
             sh.gather({} if rank == 1 else local, len(frames), error="out of memory" if rank == 1 else None)
             ok = False

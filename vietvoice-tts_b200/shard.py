@@ -71,18 +71,53 @@ class Sharder:
             if error is not None:
                 raise RuntimeError(error)
             return dict(local)
+        import torch
         import torch.distributed as dist
-        parts: List[Optional[dict]] = [None] * self.world
         mine: dict = {int(k): np.asarray(v) for k, v in local.items()}
-        if error is not None:
-            mine = {"__error__": f"rank {self.rank}: {error}"}
-        dist.all_gather_object(parts, mine, group=self.group)
-        failed = [p["__error__"] for p in parts if p and "__error__" in p]
-        if failed:
-            raise RuntimeError("; ".join(failed))
+        # Phase 1 — one small tensor per rank: sample count and rank (ndim) of every chunk it holds, plus a status word
+        # (0 = int16 waves with unit leading dimensions: the fast path, 1 = something else: pickle it, 2 = failed).
+        meta = torch.full((2 * n_chunks + 1,), -1, dtype=torch.int64)
+        plain = all(0 <= k < n_chunks and v.dtype == np.int16 and v.ndim >= 1 and v.size == v.shape[-1]
+                    for k, v in mine.items())
+        for k, v in mine.items():
+            if 0 <= k < n_chunks:
+                meta[k], meta[n_chunks + k] = v.shape[-1], v.ndim
+        meta[2 * n_chunks] = 2 if error is not None else (0 if plain else 1)
+        metas = [torch.empty_like(meta) for _ in range(self.world)]
+        dist.all_gather(metas, meta, group=self.group)
+        status = max(int(m[2 * n_chunks]) for m in metas)
         merged: Dict[int, np.ndarray] = {}
-        for p in parts:
-            merged.update(p or {})
+        if status == 0:
+            # Phase 2 — the waves themselves as ONE int16 tensor per rank (chunks in ascending index order, padded to the
+            # largest rank): no pickling, one collective (at 8 ranks / 349 s of audio the pickled form took ~20 ms).
+            sizes = [int(m[:n_chunks].clamp(min=0).sum()) for m in metas]
+            width = max(max(sizes), 1)
+            buf = torch.zeros(width, dtype=torch.int16)
+            off = 0
+            for k in sorted(mine):
+                n = mine[k].shape[-1]
+                buf[off:off + n] = torch.from_numpy(np.ascontiguousarray(mine[k]).reshape(-1))
+                off += n
+            outs = [torch.empty(width, dtype=torch.int16) for _ in range(self.world)]
+            # (gloo has no int16: the same memory travels as bytes)
+            dist.all_gather([o.view(torch.uint8) for o in outs], buf.view(torch.uint8), group=self.group)
+            for m, o in zip(metas, outs):
+                flat, off = o.numpy(), 0
+                for k in range(n_chunks):
+                    n = int(m[k])
+                    if n >= 0:
+                        merged[k] = flat[off:off + n].reshape((1,) * (int(m[n_chunks + k]) - 1) + (n,)).copy()
+                        off += n
+        else:
+            parts: List[Optional[dict]] = [None] * self.world
+            if error is not None:
+                mine = {"__error__": f"rank {self.rank}: {error}"}
+            dist.all_gather_object(parts, mine, group=self.group)
+            failed = [p["__error__"] for p in parts if p and "__error__" in p]
+            if failed:
+                raise RuntimeError("; ".join(failed))
+            for p in parts:
+                merged.update(p or {})
         missing = [i for i in range(n_chunks) if i not in merged]
         if missing:
             raise RuntimeError(f"chunks {missing} were not produced by any rank")
