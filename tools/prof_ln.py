@@ -1,4 +1,4 @@
-"""LayerNorm-modulate alone at the bench shape (M 24272 x 1024): us per launch and GB/s; variants via VVB200_LN_VARIANT."""
+"""LayerNorm-modulate alone at the bench shape (M 24272 x 1024): us per launch and GB/s; median of 20 launches with the L2 flushed before each."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -27,5 +27,5 @@ for _ in range(20):
     ts.append(e0.elapsed_time(e1))
 ts.sort()
 ms = ts[len(ts) // 2]
-print(f"variant {os.environ.get('VVB200_LN_VARIANT', '0')} reverse {os.environ.get('VVB200_LN_REVERSE', '1')}: {ms*1e3:7.1f} us  {M*K*6/ms/1e6:7.1f} GB/s  rel err {err:.2e}")
+print(f"ln_modulate reverse {os.environ.get('VVB200_LN_REVERSE', '1')}: {ms*1e3:7.1f} us  {M*K*6/ms/1e6:7.1f} GB/s  rel err {err:.2e}")
 lib.vv_engine_destroy(h)

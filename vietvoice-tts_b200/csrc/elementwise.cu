@@ -74,64 +74,6 @@ ln_kernel(const float* __restrict__ x, int rows, int dim, const float* __restric
   }
 }
 
-
-// A/B variant (VVB200_LN_VARIANT): R rows per warp with all loads issued up front (more bytes in flight per thread),
-// 256-bit streaming loads that bypass L1, and the bf16 row written with 128-bit stores: each lane owns 8 consecutive
-// columns per 256-column slab instead of 4 per 128.
-template <int SLABS, int R>
-__global__ void __launch_bounds__(256)
-ln_mod_wide_kernel(const float* __restrict__ x, int rows, int dim, const float* __restrict__ shift,
-                   const float* __restrict__ scale, float eps, bf16* __restrict__ out, int reverse) {
-  pdl_trigger();
-  const int blk = reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int row0 = (blk * 8 + (threadIdx.x >> 5)) * R;
-  if (row0 >= rows) return;
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  float4 v[R][SLABS][2];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (row0 + r < rows) {
-      const float* xr = x + (size_t)(row0 + r) * dim + lane * 8;
-#pragma unroll
-      for (int i = 0; i < SLABS; ++i) ldg256_stream(xr + 256 * i, v[r][i][0], v[r][i][1]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (row0 + r >= rows) break;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < SLABS; ++i)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) s += v[r][i][h].x + v[r][i][h].y + v[r][i][h].z + v[r][i][h].w;
-    const float mean = warp_sum(s) / dim;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < SLABS; ++i)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float dx = v[r][i][h].x - mean, dy = v[r][i][h].y - mean, dz = v[r][i][h].z - mean, dw = v[r][i][h].w - mean;
-        q += dx * dx + dy * dy + dz * dz + dw * dw;
-      }
-    const float rstd = rsqrtf(warp_sum(q) / dim + eps);
-#pragma unroll
-    for (int i = 0; i < SLABS; ++i) {
-      uint32_t u[4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c4 = (256 * i + lane * 8) / 4 + h;
-        const float4 pa = __ldg(reinterpret_cast<const float4*>(shift) + c4);
-        const float4 pb = __ldg(reinterpret_cast<const float4*>(scale) + c4);
-        const float4 t = v[r][i][h];
-        u[2 * h] = pack_bf16((t.x - mean) * rstd * (1.f + pb.x) + pa.x, (t.y - mean) * rstd * (1.f + pb.y) + pa.y);
-        u[2 * h + 1] = pack_bf16((t.z - mean) * rstd * (1.f + pb.z) + pa.z, (t.w - mean) * rstd * (1.f + pb.w) + pa.w);
-      }
-      *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * dim + 256 * i + lane * 8) = make_uint4(u[0], u[1], u[2], u[3]);
-    }
-  }
-}
-
 template <bool AFFINE>
 static void launch_ln_any(const float* x, int rows, int dim, const float* a, const float* b, float eps, bf16* ob,
                           float* of, cudaStream_t st) {
@@ -154,20 +96,6 @@ static void launch_ln_any(const float* x, int rows, int dim, const float* a, con
 
 void launch_ln_mod(const float* x, int rows, int dim, const float* shift, const float* scale, float eps, bf16* out,
                    cudaStream_t st) {
-  static const int variant = [] {
-    const char* v = getenv("VVB200_LN_VARIANT");
-    return v ? atoi(v) : 0;
-  }();
-  static const int rev = [] {
-    const char* v = getenv("VVB200_LN_REVERSE");
-    return (v && v[0] == '0') ? 0 : 1;
-  }();
-  if (variant > 0 && dim == 1024 && (reinterpret_cast<uintptr_t>(x) & 31) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    if (variant == 1) launch_k(ln_mod_wide_kernel<4, 1>, (rows + 7) / 8, 256, 0, st, x, rows, dim, shift, scale, eps, out, rev);
-    else if (variant == 2) launch_k(ln_mod_wide_kernel<4, 2>, (rows + 15) / 16, 256, 0, st, x, rows, dim, shift, scale, eps, out, rev);
-    else launch_k(ln_mod_wide_kernel<4, 4>, (rows + 31) / 32, 256, 0, st, x, rows, dim, shift, scale, eps, out, rev);
-    return;
-  }
   launch_ln_any<false>(x, rows, dim, shift, scale, eps, out, nullptr, st);
 }
 void launch_ln_affine(const float* x, int rows, int dim, const float* g, const float* b, float eps, bf16* out_bf16,
