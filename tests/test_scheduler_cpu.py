@@ -97,6 +97,24 @@ def test_rank_ownership_and_validation():
         bad = sch.submit("3:1", speed=9.0)       # request 3 -> this rank; speed outside ModelConfig's range
         with pytest.raises(ValueError):
             bad.result(timeout=10)
+        # an explicit owner (front-end balancer) overrides the counter rule
+        assert sch.submit("4:1", owner=0).result(timeout=10) is None
+        assert sch.submit("5:1", owner=1).result(timeout=10)[0].shape == (4,)
+        assert sch.submit("6:1", owner=3).result(timeout=10)[0].shape == (4,)     # owner taken modulo world
+
+
+def test_dispatch_requests_balances_and_is_deterministic():
+    from vietvoice_tts_b200.shard import dispatch_requests
+    rng = np.random.default_rng(5)
+    costs = [float(rng.integers(20, 300) * rng.choice([15, 31, 63])) for _ in range(384)]
+    for world in (1, 2, 8):
+        own = dispatch_requests(costs, world)
+        assert own == dispatch_requests(costs, world) and set(own) <= set(range(world))
+        load = [sum(c for c, o in zip(costs, own) if o == r) for r in range(world)]
+        rr = [sum(costs[i] for i in range(len(costs)) if i % world == r) for r in range(world)]
+        assert max(load) <= max(rr) + 1e-9                       # never worse than round robin on this stream
+        assert max(load) / (sum(load) / world) < 1.03            # online least-loaded: within a few % of the mean
+    assert dispatch_requests([], 4) == [] and dispatch_requests([1.0, 1.0, 1.0], 2) == [0, 1, 0]
 
 
 def test_submit_is_thread_safe():

@@ -1,6 +1,7 @@
 """BASELINE config 5 as a measurement: a Poisson stream of API-style requests (voices swept over the metadata table,
 NFE 16 / 32 / 64, texts of one to a few sentences) through the request scheduler on ONE GPU; with torchrun every
-rank runs the scheduler for the requests it owns (request i -> rank i % world, no collective).
+rank runs the scheduler for the requests it owns (owner = the rank with the least estimated work at the request's
+arrival, computed identically on every rank; no collective).
 
 Prints one JSON line: aggregate audio-seconds per second over the makespan, p50 / p95 request latency
 (submit -> waveform), micro-batch statistics.  Random-init weights of the FULL architecture, synthetic 6 s prompts.
@@ -54,8 +55,16 @@ def make_requests(n, rate, seed):
     return reqs
 
 
+def request_owners(reqs, world):
+    """Front-end balancing: estimated work of a request = characters of text x Euler steps; requests go, in arrival
+    order, to the rank with the least work accepted so far (shard.dispatch_requests) — the same on every rank."""
+    from vietvoice_tts_b200.shard import dispatch_requests
+    return dispatch_requests([len(text) * (nfe - 1) for _, text, _, nfe in reqs], world)
+
+
 def run_stream(tts, reqs, rank=0, world=1, max_batch_chunks=8, max_batch_frames=8 * 1800, warm=True):
-    """Plays `reqs` through a RequestScheduler on this rank (request i belongs to rank i % world).
+    """Plays `reqs` through a RequestScheduler on this rank (owner of request i: request_owners(); VVB200_STREAM_RR=1
+    falls back to i % world).
     -> dict(audio_s, work_s, makespan_s, lat, errs, batches, chunks); work_s = audio seconds weighted by
     (nfe - 1) / 31, i.e. in units of NFE-32 work (an NFE-64 second costs 63/31 of an NFE-32 second)."""
     from vietvoice_tts_b200.host.scheduler import RequestScheduler
@@ -64,6 +73,7 @@ def run_stream(tts, reqs, rank=0, world=1, max_batch_chunks=8, max_batch_frames=
             for nfe in NFE_CHOICES:
                 sch.submit(SENTENCES[0], nfe=nfe).result(timeout=600)
     lat, audio_s, work_s, errs = [], [], [], []
+    owners = [i % world for i in range(len(reqs))] if os.environ.get("VVB200_STREAM_RR") == "1" else request_owners(reqs, world)
     with RequestScheduler(tts, max_batch_chunks=max_batch_chunks, max_batch_frames=max_batch_frames,
                           rank=rank, world=world) as sch:
         lock = threading.Lock()
@@ -77,7 +87,7 @@ def run_stream(tts, reqs, rank=0, world=1, max_batch_chunks=8, max_batch_frames=
             t0 = time.time()
             try:
                 res = sch.submit(text, gender=v["gender"], group=v["group"], area=v["area"], emotion=v["emotion"],
-                                 nfe=nfe).result(600)
+                                 nfe=nfe, owner=owners[i]).result(600)
             except Exception as ex:
                 with lock:
                     errs.append(repr(ex))

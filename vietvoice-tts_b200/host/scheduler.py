@@ -115,14 +115,16 @@ class RequestScheduler:
     def submit(self, text: str, gender: Optional[str] = None, group: Optional[str] = None, area: Optional[str] = None,
                emotion: Optional[str] = None, sample_iteration: Optional[int] = None,
                reference_audio: Optional[str] = None, reference_text: Optional[str] = None, nfe: Optional[int] = None,
-               speed: Optional[float] = None, seed: Optional[int] = None) -> Future:
-        """-> Future of (int16 waveform, seconds since submit).  Requests not owned by this rank resolve to None."""
+               speed: Optional[float] = None, seed: Optional[int] = None, owner: Optional[int] = None) -> Future:
+        """-> Future of (int16 waveform, seconds since submit).  Requests not owned by this rank resolve to None.
+        owner: the rank a front-end balancer chose for this request (`shard.dispatch_requests`); default: request
+        counter modulo world."""
         cfg = self.tts.config
         with self._id_lock:
             rid = self._next_id
             self._next_id += 1
         fut: Future = Future()
-        if not self.owns(rid):
+        if (owner % self.world != self.rank) if owner is not None else not self.owns(rid):
             fut.set_result(None)
             return fut
         if nfe is not None and not (2 <= int(nfe) <= MAX_NFE):

@@ -46,6 +46,20 @@ def imbalance(total_frames: Sequence[int], world: int, arch: ArchConfig = FULL) 
     return max(loads) / mean if mean > 0 else 1.0
 
 
+def dispatch_requests(costs: Sequence[float], world: int) -> List[int]:
+    """Owner rank of each request of a stream, decided in ARRIVAL order (an online front-end balancer: request i goes to
+    the rank with the least estimated work accepted so far; ties to the lowest rank).  Deterministic, so every rank of a
+    job that replays the same stream computes the same owners without talking to the others.  Against `i % world` it
+    keeps the slowest rank's makespan near the mean when request sizes and NFE differ by an order of magnitude."""
+    load = [0.0] * max(world, 1)
+    owners: List[int] = []
+    for c in costs:
+        r = min(range(len(load)), key=lambda k: (load[k], k))
+        owners.append(r)
+        load[r] += float(c)
+    return owners
+
+
 class Sharder:
     def __init__(self, rank: int = 0, world: int = 1, group=None, arch: ArchConfig = FULL):
         self.rank, self.world, self.group, self.arch = rank, world, group, arch
