@@ -23,9 +23,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#ifndef VV_GEMM_ABLATE
-#define VV_GEMM_ABLATE 0
-#endif
 #ifndef VV_GEMM_TIMING
 #define VV_GEMM_TIMING 0
 #endif
@@ -313,15 +310,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-#if VV_GEMM_ABLATE == 1
-            tma_store_2d(&tmO, buf, nbase + c0 * 32 + q * STG_COLS, row0);       // ablation: plain store, no read-modify-write
-            tma_store_commit();
-#elif VV_GEMM_ABLATE == 2
-            (void)buf;                                                            // ablation: the delta is not written at all
-#else
             tma_reduce_add_2d(&tmO, buf, nbase + c0 * 32 + q * STG_COLS, row0);
             tma_store_commit();
-#endif
           }
         }
       } else {
